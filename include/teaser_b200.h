@@ -1,0 +1,174 @@
+/*
+ * teaser_b200.h — C-ABI of the B200-native TEASER++ registration hot path.
+ *
+ * This is the drop-in boundary: plain C, caller-owned buffers, no STL / Eigen / torch types.
+ * The reference has no FFI layer of its own; each entry point below names the
+ * reference function(s) it replaces (paths relative to the reference tree).  The C++ facade
+ * `teaser::RobustRegistrationSolver` (teaser-plusplus_b200/include/teaser/registration.h) and the
+ * Python module `teaserpp_python` call exactly these symbols; INTEGRATION.md shows the binding a
+ * TEASER++ maintainer would add.
+ *
+ * Conventions
+ *   - Points are 3xN column-major double == N contiguous (x,y,z) triples, i.e. the memory of an
+ *     Eigen::Matrix<double,3,Dynamic> (teaser/src/registration.cc:568-570).
+ *   - 3x3 rotations are column-major (Eigen::Matrix3d).
+ *   - The inlier graph is a packed, symmetric adjacency bitset: n rows of `tzr_words_per_row(n)`
+ *     little-endian uint64 words; bit j of row i is set iff TIM (i,j) passed the scale test
+ *     (replaces teaser::Graph's vector<vector<int>>, teaser/include/teaser/graph.h:29-207).
+ *   - Every function returns 0 on success or a negative tzr_status; no exceptions cross the ABI.
+ *   - "_dev" variants take DEVICE pointers and enqueue on the context's stream without
+ *     synchronising (tzr_ctx_synchronize does); the plain variants take HOST pointers and are
+ *     synchronous, host<->device copies included.
+ *   - A context owns one CUDA device, one stream and a growable workspace; it is not thread-safe,
+ *     distinct contexts are independent.  There is NO CPU fallback: without a usable CUDA device
+ *     tzr_ctx_create fails with TZR_ERR_NO_DEVICE.
+ */
+#ifndef TEASER_B200_H_
+#define TEASER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TZR_ABI_VERSION 1
+
+typedef enum tzr_status {
+  TZR_OK = 0,
+  TZR_ERR_INVALID_ARG = -1,
+  TZR_ERR_NO_DEVICE = -2,
+  TZR_ERR_CUDA = -3,
+  TZR_ERR_ALLOC = -4,
+  TZR_ERR_UNSUPPORTED = -5,
+  TZR_ERR_TOO_LARGE = -6
+} tzr_status;
+
+/* teaser::RobustRegistrationSolver::Params (teaser/include/teaser/registration.h:419-514).
+ * Enum values are the reference's (registration.h:382-412). */
+typedef struct tzr_params {
+  double noise_bound;                    /* default 0.01 */
+  double cbar2;                          /* default 1 */
+  int32_t estimate_scaling;              /* default 1 (true) */
+  int32_t rotation_estimation_algorithm; /* 0 GNC_TLS (default), 1 FGR, 2 QUATRO */
+  double rotation_gnc_factor;            /* default 1.4 */
+  uint64_t rotation_max_iterations;      /* default 100 */
+  double rotation_cost_threshold;        /* default 1e-6 */
+  int32_t rotation_tim_graph;            /* 0 CHAIN (default), 1 COMPLETE */
+  int32_t inlier_selection_mode;         /* 0 PMC_EXACT (default), 1 PMC_HEU, 2 KCORE_HEU, 3 NONE */
+  double kcore_heuristic_threshold;      /* default 0.5 */
+  int32_t use_max_clique;                /* deprecated, default 1 */
+  int32_t max_clique_exact_solution;     /* deprecated, default 1 */
+  double max_clique_time_limit;          /* seconds, default 3600 */
+  int32_t max_clique_num_threads;        /* ignored on the GPU */
+  int32_t reserved;
+} tzr_params;
+
+/* teaser::RegistrationSolution (registration.h:32-39) plus diagnostics the getters expose. */
+typedef struct tzr_solution {
+  int32_t valid;                  /* solution_.valid (registration.cc:643-647,734) */
+  int32_t clique_size;            /* getInlierMaxClique().size() */
+  double scale;
+  double translation[3];
+  double rotation[9];             /* column-major */
+  int32_t clique_proven_optimal;  /* 1: maximum clique proven; 0: heuristic mode or budget hit */
+  int32_t gnc_iterations;         /* loop bodies entered by the GNC rotation solver */
+  double gnc_cost;                /* getGNCRotationCostAtTermination() */
+  int32_t n_rotation_inliers;
+  int32_t n_translation_inliers;
+  int64_t n_edges;                /* edges of the inlier graph */
+  double stage_ms[8];             /* filled by tzr_solve only: 0 h2d, 1 graph, 2 clique, 3 rot+trans, 4 d2h, 6 total */
+} tzr_solution;
+
+typedef struct tzr_ctx tzr_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int tzr_abi_version(void);
+const char* tzr_status_string(int status);
+/* Last CUDA error text seen by this context (empty string if none). */
+const char* tzr_last_error(const tzr_ctx* ctx);
+/* Fill `p` with the reference's Params defaults (registration.h:419-514). */
+void tzr_params_default(tzr_params* p);
+/* device < 0: current device.  Fails (TZR_ERR_NO_DEVICE) when no CUDA device is usable. */
+int tzr_ctx_create(int device, tzr_ctx** out);
+int tzr_ctx_destroy(tzr_ctx* ctx);
+/* Use an existing CUDA stream (cudaStream_t as void*) instead of the context's own. */
+int tzr_ctx_set_stream(tzr_ctx* ctx, void* cuda_stream);
+int tzr_ctx_synchronize(tzr_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t tzr_ctx_kernel_launches(const tzr_ctx* ctx);
+/* 64-bit words per adjacency row: ceil(n/64). */
+int tzr_words_per_row(int n);
+
+/* ---- stage 1: TIMs + scale consistency + inlier graph ---------------------------------------
+ * Replaces computeTIMs (registration.cc:512-551) x2, ScaleInliersSelector::solveForScale
+ * (registration.cc:427-443) and the Graph::addEdge loop (registration.cc:614-619) — fused, the
+ * N(N-1)/2 TIMs are never materialised.  beta = 2*noise_bound*sqrt(cbar2).
+ * adj_bits: n * tzr_words_per_row(n) uint64 (fully overwritten); degree: n int32 (may be NULL). */
+int tzr_graph_build(tzr_ctx* ctx, const double* src_3xN, const double* dst_3xN, int n, double beta,
+                    uint64_t* adj_bits, int32_t* degree, int64_t* n_edges);
+
+/* ---- stage 2: maximum clique ----------------------------------------------------------------
+ * Replaces teaser::MaxCliqueSolver::findMaxClique (teaser/src/graph.cc:12-125) including the PMC
+ * library calls it makes.  mode: 0 PMC_EXACT, 1 PMC_HEU, 2 KCORE_HEU.  clique: capacity n, returned
+ * sorted ascending (solve() sorts it, registration.cc:636).  *proven_optimal = 1 when the search
+ * proved maximality. */
+int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, double kcore_heuristic_threshold,
+                   double time_limit_s, int32_t* clique, int32_t* clique_size, int32_t* proven_optimal);
+
+/* ---- stage 3: GNC-TLS rotation --------------------------------------------------------------
+ * Replaces GNCTLSRotationSolver::solveForRotation (registration.cc:764-866) + utils::svdRot
+ * (teaser/include/teaser/utils.h:121-136).  inlier_mask (m bytes) and the scalar outputs may be NULL. */
+int tzr_gnc_tls_rotation(tzr_ctx* ctx, const double* src_3xM, const double* dst_3xM, int m, double noise_bound,
+                         double gnc_factor, uint64_t max_iterations, double cost_threshold, double* R_colmajor9,
+                         uint8_t* inlier_mask, double* cost_at_termination, int32_t* iterations);
+
+/* ---- stage 4: TLS translation ---------------------------------------------------------------
+ * Replaces TLSTranslationSolver::solveForTranslation (registration.cc:445-471): per-axis
+ * ScalarTLSEstimator::estimate on dst - src with range noise_bound*sqrt(cbar2). */
+int tzr_tls_translation(tzr_ctx* ctx, const double* src_3xM, const double* dst_3xM, int m, double noise_bound,
+                        double cbar2, double* t3, uint8_t* inlier_mask);
+
+/* ScalarTLSEstimator::estimate (registration.cc:21-88), standalone. */
+int tzr_scalar_tls(tzr_ctx* ctx, const double* x, const double* ranges, int64_t m, double* estimate,
+                   uint8_t* inliers);
+
+/* ---- whole path -----------------------------------------------------------------------------
+ * Replaces RobustRegistrationSolver::solve(src, dst) (registration.cc:568-737) for one problem
+ * (tzr_solve) or B independent problems (tzr_solve_batch).  All intermediates stay on the device.
+ * clique: capacity n, sorted.  rot_inliers: capacity = number of rotation TIMs (clique size for
+ * CHAIN).  trans_inliers: capacity clique size (n is always enough).  Optional outputs may be NULL. */
+int tzr_solve(tzr_ctx* ctx, const tzr_params* params, const double* src_3xN, const double* dst_3xN, int n,
+              tzr_solution* solution, int32_t* clique, uint8_t* rot_inliers, uint8_t* trans_inliers);
+
+/* B problems, problem b has n[b] correspondences at src[b] / dst[b] (host pointers).
+ * cliques: B*max_n int32, problem b's clique at cliques + b*max_n (may be NULL). */
+int tzr_solve_batch(tzr_ctx* ctx, const tzr_params* params, int B, const int32_t* n, const double* const* src,
+                    const double* const* dst, tzr_solution* solutions, int32_t* cliques, int max_n);
+
+/* Device-resident batch of equally sized problems: src_dev/dst_dev hold B*n*3 doubles each
+ * (problem-major), solutions_dev B tzr_solution, cliques_dev B*n int32 (may be NULL).  Asynchronous on
+ * the context's stream; this is what bench.py's kernel-only timing and the multi-GPU shards drive. */
+int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, const double* src_dev,
+                        const double* dst_dev, tzr_solution* solutions_dev, int32_t* cliques_dev);
+
+/* Retrieve the adjacency bitset / degrees of problem b of the most recent solve on this context
+ * (lazy materialisation of getInlierGraph(), registration.h:772). Host pointers. */
+int tzr_last_graph(tzr_ctx* ctx, int b, uint64_t* adj_bits, int32_t* degree);
+
+/* Graph-stage timing of the most recent tzr_solve_batch_dev, in milliseconds, measured with CUDA
+ * events on the context's stream (for the roofline line in bench.py). Requires a prior synchronize. */
+int tzr_last_stage_ms(tzr_ctx* ctx, double* prep_ms, double* graph_ms, double* clique_ms, double* rot_trans_ms);
+
+/* Debug/verification switches: bit 0 = force the pure-FP64 graph predicate (no FP32 filter),
+ * bit 1 = verify the FP32 filter against FP64 for every pair and count mismatches. */
+int tzr_ctx_set_flags(tzr_ctx* ctx, uint32_t flags);
+int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx);
+/* Number of pairs of the most recent graph build that needed the exact FP64 re-check. */
+int64_t tzr_ctx_filter_rechecks(tzr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEASER_B200_H_ */

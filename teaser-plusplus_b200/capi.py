@@ -1,0 +1,310 @@
+"""ctypes binding of the C-ABI product library (csrc/libteaser_b200.so, include/teaser_b200.h).
+
+There is no CPU fallback: every entry point raises if the library is missing or no CUDA device is
+usable.  Points are (N,3) float64 C-contiguous numpy arrays (== the reference's column-major 3xN).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(CSRC_DIR, "libteaser_b200.so")
+
+
+class TzrError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """tzr_params == teaser::RobustRegistrationSolver::Params (registration.h:419-514)."""
+    _fields_ = [
+        ("noise_bound", C.c_double),
+        ("cbar2", C.c_double),
+        ("estimate_scaling", C.c_int32),
+        ("rotation_estimation_algorithm", C.c_int32),
+        ("rotation_gnc_factor", C.c_double),
+        ("rotation_max_iterations", C.c_uint64),
+        ("rotation_cost_threshold", C.c_double),
+        ("rotation_tim_graph", C.c_int32),
+        ("inlier_selection_mode", C.c_int32),
+        ("kcore_heuristic_threshold", C.c_double),
+        ("use_max_clique", C.c_int32),
+        ("max_clique_exact_solution", C.c_int32),
+        ("max_clique_time_limit", C.c_double),
+        ("max_clique_num_threads", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class Solution(C.Structure):
+    """tzr_solution == teaser::RegistrationSolution (registration.h:32-39) + diagnostics."""
+    _fields_ = [
+        ("valid", C.c_int32),
+        ("clique_size", C.c_int32),
+        ("scale", C.c_double),
+        ("translation", C.c_double * 3),
+        ("rotation", C.c_double * 9),
+        ("clique_proven_optimal", C.c_int32),
+        ("gnc_iterations", C.c_int32),
+        ("gnc_cost", C.c_double),
+        ("n_rotation_inliers", C.c_int32),
+        ("n_translation_inliers", C.c_int32),
+        ("n_edges", C.c_int64),
+        ("stage_ms", C.c_double * 8),
+    ]
+
+    @property
+    def R(self):
+        return np.array(self.rotation[:]).reshape(3, 3).T.copy()
+
+    @property
+    def t(self):
+        return np.array(self.translation[:])
+
+
+SOLUTION_DTYPE = np.dtype([
+    ("valid", np.int32), ("clique_size", np.int32), ("scale", np.float64), ("translation", np.float64, (3,)),
+    ("rotation", np.float64, (9,)), ("clique_proven_optimal", np.int32), ("gnc_iterations", np.int32),
+    ("gnc_cost", np.float64), ("n_rotation_inliers", np.int32), ("n_translation_inliers", np.int32),
+    ("n_edges", np.int64), ("stage_ms", np.float64, (8,))], align=True)
+assert SOLUTION_DTYPE.itemsize == C.sizeof(Solution), (SOLUTION_DTYPE.itemsize, C.sizeof(Solution))
+
+_lib = None
+
+_SYMBOLS = [
+    "tzr_abi_version", "tzr_status_string", "tzr_last_error", "tzr_params_default", "tzr_ctx_create",
+    "tzr_ctx_destroy", "tzr_ctx_set_stream", "tzr_ctx_synchronize", "tzr_ctx_kernel_launches", "tzr_words_per_row",
+    "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_tls_translation", "tzr_scalar_tls",
+    "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
+    "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks",
+]
+
+
+def build(verbose: bool = False):
+    """Compile csrc/*.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR] + ([] if verbose else ["-s"])
+    subprocess.check_call(cmd)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TzrError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    dp, u8p, i32p, i64p, u64p = (C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_uint64))
+    vp = C.c_void_p
+    L.tzr_abi_version.restype = C.c_int
+    L.tzr_status_string.restype = C.c_char_p
+    L.tzr_status_string.argtypes = [C.c_int]
+    L.tzr_last_error.restype = C.c_char_p
+    L.tzr_last_error.argtypes = [vp]
+    L.tzr_params_default.argtypes = [C.POINTER(Params)]
+    L.tzr_params_default.restype = None
+    L.tzr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.tzr_ctx_destroy.argtypes = [vp]
+    L.tzr_ctx_set_stream.argtypes = [vp, vp]
+    L.tzr_ctx_synchronize.argtypes = [vp]
+    L.tzr_ctx_kernel_launches.argtypes = [vp]
+    L.tzr_ctx_kernel_launches.restype = C.c_int64
+    L.tzr_words_per_row.argtypes = [C.c_int]
+    L.tzr_graph_build.argtypes = [vp, dp, dp, C.c_int, C.c_double, u64p, i32p, i64p]
+    L.tzr_max_clique.argtypes = [vp, u64p, C.c_int, C.c_int, C.c_double, C.c_double, i32p, i32p, i32p]
+    L.tzr_gnc_tls_rotation.argtypes = [vp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_double, dp, u8p,
+                                       dp, i32p]
+    L.tzr_tls_translation.argtypes = [vp, dp, dp, C.c_int, C.c_double, C.c_double, dp, u8p]
+    L.tzr_scalar_tls.argtypes = [vp, dp, dp, C.c_int64, dp, u8p]
+    L.tzr_solve.argtypes = [vp, C.POINTER(Params), dp, dp, C.c_int, C.POINTER(Solution), i32p, u8p, u8p]
+    L.tzr_solve_batch.argtypes = [vp, C.POINTER(Params), C.c_int, i32p, C.POINTER(dp), C.POINTER(dp),
+                                  C.POINTER(Solution), i32p, C.c_int]
+    L.tzr_solve_batch_dev.argtypes = [vp, C.POINTER(Params), C.c_int, C.c_int, vp, vp, vp, vp]
+    L.tzr_last_graph.argtypes = [vp, C.c_int, u64p, i32p]
+    L.tzr_last_stage_ms.argtypes = [vp, dp, dp, dp, dp]
+    L.tzr_ctx_set_flags.argtypes = [vp, C.c_uint32]
+    L.tzr_ctx_filter_mismatches.argtypes = [vp]
+    L.tzr_ctx_filter_mismatches.restype = C.c_int64
+    L.tzr_ctx_filter_rechecks.argtypes = [vp]
+    L.tzr_ctx_filter_rechecks.restype = C.c_int64
+    for s in _SYMBOLS:
+        getattr(L, s)  # raises AttributeError if the header and the library disagree
+    _lib = L
+    return L
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().tzr_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("points must be (N,3)")
+    return a
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Context:
+    """One CUDA device + stream + workspace (tzr_ctx)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        rc = lib().tzr_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            raise TzrError(f"tzr_ctx_create failed: {lib().tzr_status_string(rc).decode()}")
+
+    def close(self):
+        if self._h:
+            lib().tzr_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TzrError(f"{lib().tzr_status_string(rc).decode()}: {lib().tzr_last_error(self._h).decode()}")
+
+    # -- utilities
+    def set_flags(self, flags: int):
+        self._ck(lib().tzr_ctx_set_flags(self._h, flags))
+
+    def filter_mismatches(self) -> int:
+        return int(lib().tzr_ctx_filter_mismatches(self._h))
+
+    def filter_rechecks(self) -> int:
+        return int(lib().tzr_ctx_filter_rechecks(self._h))
+
+    def kernel_launches(self) -> int:
+        return int(lib().tzr_ctx_kernel_launches(self._h))
+
+    def synchronize(self):
+        self._ck(lib().tzr_ctx_synchronize(self._h))
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(lib().tzr_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def last_stage_ms(self):
+        v = (C.c_double * 4)()
+        self._ck(lib().tzr_last_stage_ms(self._h, C.byref(v, 0), C.byref(v, 8), C.byref(v, 16), C.byref(v, 24)))
+        return dict(prep=v[0], graph=v[1], clique=v[2], rot_trans=v[3])
+
+    # -- stages
+    def graph_build(self, src, dst, beta):
+        s, d = _pts(src), _pts(dst)
+        n = s.shape[0]
+        W = lib().tzr_words_per_row(n)
+        bits = np.zeros((n, W), dtype=np.uint64)
+        deg = np.zeros(n, dtype=np.int32)
+        ne = C.c_int64()
+        self._ck(lib().tzr_graph_build(self._h, _p(s, C.c_double), _p(d, C.c_double), n, beta, _p(bits, C.c_uint64),
+                                       _p(deg, C.c_int32), C.byref(ne)))
+        return bits, deg, int(ne.value)
+
+    def max_clique(self, bits, n, mode=0, kcore_thr=0.5, time_limit=3600.0):
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        out = np.zeros(n, dtype=np.int32)
+        m = C.c_int32()
+        proven = C.c_int32()
+        self._ck(lib().tzr_max_clique(self._h, _p(bits, C.c_uint64), n, mode, kcore_thr, time_limit,
+                                      _p(out, C.c_int32), C.byref(m), C.byref(proven)))
+        return out[:m.value].copy(), bool(proven.value)
+
+    def gnc_tls_rotation(self, src, dst, noise_bound, gnc_factor=1.4, max_iterations=100, cost_threshold=1e-6):
+        s, d = _pts(src), _pts(dst)
+        m = s.shape[0]
+        R = np.zeros(9)
+        mask = np.zeros(m, dtype=np.uint8)
+        cost = C.c_double()
+        it = C.c_int32()
+        self._ck(lib().tzr_gnc_tls_rotation(self._h, _p(s, C.c_double), _p(d, C.c_double), m, noise_bound, gnc_factor,
+                                            int(max_iterations), cost_threshold, _p(R, C.c_double),
+                                            _p(mask, C.c_uint8), C.byref(cost), C.byref(it)))
+        return dict(R=R.reshape(3, 3).T.copy(), inliers=mask.astype(bool), cost=cost.value, iterations=it.value)
+
+    def tls_translation(self, src, dst, noise_bound, cbar2=1.0):
+        s, d = _pts(src), _pts(dst)
+        m = s.shape[0]
+        t = np.zeros(3)
+        mask = np.zeros(m, dtype=np.uint8)
+        self._ck(lib().tzr_tls_translation(self._h, _p(s, C.c_double), _p(d, C.c_double), m, noise_bound, cbar2,
+                                           _p(t, C.c_double), _p(mask, C.c_uint8)))
+        return t, mask.astype(bool)
+
+    def scalar_tls(self, x, ranges):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.ascontiguousarray(ranges, dtype=np.float64)
+        est = C.c_double()
+        inl = np.zeros(x.size, dtype=np.uint8)
+        self._ck(lib().tzr_scalar_tls(self._h, _p(x, C.c_double), _p(r, C.c_double), x.size, C.byref(est),
+                                      _p(inl, C.c_uint8)))
+        return est.value, inl.astype(bool)
+
+    # -- whole path
+    def solve(self, src, dst, params: Params):
+        s, d = _pts(src), _pts(dst)
+        n = s.shape[0]
+        sol = Solution()
+        clique = np.zeros(n, dtype=np.int32)
+        rm = np.zeros(n, dtype=np.uint8)
+        tm = np.zeros(n, dtype=np.uint8)
+        self._ck(lib().tzr_solve(self._h, C.byref(params), _p(s, C.c_double), _p(d, C.c_double), n, C.byref(sol),
+                                 _p(clique, C.c_int32), _p(rm, C.c_uint8), _p(tm, C.c_uint8)))
+        m = sol.clique_size
+        return dict(sol=sol, valid=bool(sol.valid), scale=sol.scale, R=sol.R, t=sol.t, clique=clique[:m].copy(),
+                    rot_inliers=rm[:m].astype(bool), trans_inliers=tm[:m].astype(bool),
+                    gnc_iterations=sol.gnc_iterations, proven=bool(sol.clique_proven_optimal),
+                    n_edges=int(sol.n_edges), stage_ms=list(sol.stage_ms))
+
+    def solve_batch(self, srcs, dsts, params: Params):
+        """srcs/dsts: lists of (N_b,3) arrays (host). Returns (solutions structured array, list of cliques)."""
+        B = len(srcs)
+        S = [_pts(a) for a in srcs]
+        D = [_pts(a) for a in dsts]
+        ns = np.array([a.shape[0] for a in S], dtype=np.int32)
+        max_n = int(ns.max())
+        dp = C.POINTER(C.c_double)
+        sp = (dp * B)(*[_p(a, C.c_double) for a in S])
+        dpp = (dp * B)(*[_p(a, C.c_double) for a in D])
+        sols = np.zeros(B, dtype=SOLUTION_DTYPE)
+        cl = np.zeros((B, max_n), dtype=np.int32)
+        self._ck(lib().tzr_solve_batch(self._h, C.byref(params), B, _p(ns, C.c_int32), sp, dpp,
+                                       sols.ctypes.data_as(C.POINTER(Solution)), _p(cl, C.c_int32), max_n))
+        cliques = [cl[b, :max(0, int(sols[b]["clique_size"]))].copy() for b in range(B)]
+        return sols, cliques
+
+    def solve_batch_dev(self, params: Params, B: int, n: int, src_ptr: int, dst_ptr: int, sol_ptr: int,
+                        clique_ptr: int = 0):
+        """Device pointers (e.g. torch tensors' data_ptr()); asynchronous on the context's stream."""
+        self._ck(lib().tzr_solve_batch_dev(self._h, C.byref(params), B, n, C.c_void_p(src_ptr), C.c_void_p(dst_ptr),
+                                           C.c_void_p(sol_ptr), C.c_void_p(clique_ptr) if clique_ptr else None))
+
+    def last_graph(self, b: int, n: int):
+        W = lib().tzr_words_per_row(n)
+        bits = np.zeros((n, W), dtype=np.uint64)
+        deg = np.zeros(n, dtype=np.int32)
+        self._ck(lib().tzr_last_graph(self._h, b, _p(bits, C.c_uint64), _p(deg, C.c_int32)))
+        return bits, deg
+
+
+def rotation_from_solution_record(rec) -> np.ndarray:
+    return np.asarray(rec["rotation"]).reshape(3, 3).T.copy()

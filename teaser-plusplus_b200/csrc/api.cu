@@ -1,0 +1,685 @@
+// C-ABI of libteaser_b200.so: context, workspace, stage entry points and the fused batch solve.
+// See include/teaser_b200.h for the contract and the reference functions each symbol replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tzr_internal.cuh"
+
+using namespace tzr;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct tzr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string last_error;
+  int64_t launches = 0;
+  uint32_t flags = 0;
+  int num_sms = 148;
+  // device buffers (grow-only)
+  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, alive_cnt, root_ctr, lock, flg, stack, cv,
+      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc;
+  // pinned host staging
+  void* h_pin = nullptr;
+  size_t h_pin_cap = 0;
+  // last batch geometry
+  Batch last{};
+  bool have_last = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+#define CK(call)                                                                  \
+  do {                                                                            \
+    cudaError_t _e = (call);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);       \
+      return TZR_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+int ensure(tzr_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return TZR_OK;
+  if (b.p) {
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return TZR_ERR_ALLOC;
+  }
+  b.cap = want;
+  return TZR_OK;
+}
+
+int ensure_pinned(tzr_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_pin_cap) return TZR_OK;
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  ctx->h_pin = nullptr;
+  ctx->h_pin_cap = 0;
+  cudaError_t e = cudaMallocHost(&ctx->h_pin, bytes + bytes / 8 + 256);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+    return TZR_ERR_ALLOC;
+  }
+  ctx->h_pin_cap = bytes + bytes / 8 + 256;
+  return TZR_OK;
+}
+
+int next_pow2_host(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// effective inlier selection mode (registration.cc:574-583)
+int effective_mode(const tzr_params& p) {
+  int mode = p.inlier_selection_mode;
+  if (!p.use_max_clique) mode = 3;
+  if (!p.max_clique_exact_solution) mode = 1;
+  return mode;
+}
+
+// Size the workspace for a (B, n) batch and fill the Batch descriptor (src/dst left to the caller).
+int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
+  if (B <= 0 || n <= 0) return TZR_ERR_INVALID_ARG;
+  if (n > kMaxN) return TZR_ERR_TOO_LARGE;
+  Batch bt{};
+  bt.B = B;
+  bt.n = n;
+  const size_t Bn = (size_t)B * n;
+  const int W32 = pitch32(n);
+  int rc;
+#define ENS(buf, bytes)                                  \
+  if ((rc = ensure(ctx, ctx->buf, (bytes))) != TZR_OK) return rc;
+  if (own_points) {
+    ENS(src, Bn * 3 * sizeof(double));
+    ENS(dst, Bn * 3 * sizeof(double));
+  }
+  ENS(sf, Bn * sizeof(float4));
+  ENS(df, Bn * sizeof(float4));
+  ENS(gc, (size_t)B * sizeof(GraphConsts));
+  ENS(adj, Bn * pitch64(n) * sizeof(uint64_t));
+  ENS(deg, Bn * sizeof(int32_t));
+  ENS(nedges, (size_t)B * sizeof(unsigned long long));
+  ENS(hclq, Bn * kHeurRoots * sizeof(int32_t));
+  ENS(hsize, (size_t)B * kHeurRoots * sizeof(int32_t));
+  ENS(clq, Bn * sizeof(int32_t));
+  ENS(L, (size_t)B * sizeof(int32_t));
+  ENS(alive, (size_t)B * W32 * sizeof(uint32_t));
+  ENS(alive_cnt, (size_t)B * sizeof(int32_t));
+  ENS(root_ctr, (size_t)B * sizeof(int32_t));
+  ENS(lock, (size_t)B * sizeof(int32_t));
+  ENS(flg, (size_t)B * sizeof(int32_t));
+  // exact phase geometry: ~2 CTAs per SM over the whole batch, at least 1 CTA per problem
+  int G = (2 * ctx->num_sms + B - 1) / B;
+  if (G < 1) G = 1;
+  if (G > 2 * ctx->num_sms) G = 2 * ctx->num_sms;
+  const size_t warps = (size_t)B * G * 8;
+  const size_t level_bytes = (size_t)2 * W32 * sizeof(uint32_t);
+  size_t depth = ((size_t)1 << 30) / (warps * level_bytes);
+  if (depth > 512) depth = 512;
+  if (depth > (size_t)n) depth = (size_t)n;
+  if (depth < 16) depth = 16;
+  bt.exact_ctas = G;
+  bt.max_depth = (int)depth;
+  ENS(stack, warps * depth * level_bytes);
+  ENS(cv, warps * (size_t)n * sizeof(int32_t));
+  ENS(centry, warps * depth * sizeof(int32_t));
+  bt.sort_cap = next_pow2_host(2 * n);
+  ENS(ps, Bn * 3 * sizeof(double));
+  ENS(pd, Bn * 3 * sizeof(double));
+  ENS(wgt, Bn * sizeof(double));
+  ENS(res, Bn * sizeof(double));
+  ENS(skey, (size_t)B * 3 * bt.sort_cap * sizeof(double));
+  ENS(sidx, (size_t)B * 3 * bt.sort_cap * sizeof(int32_t));
+  ENS(sorted, Bn * sizeof(int32_t));
+  ENS(rmask, Bn);
+  ENS(tmask, Bn);
+  ENS(sol, (size_t)B * sizeof(tzr_solution));
+  ENS(dbg, 2 * sizeof(unsigned long long));
+#undef ENS
+  bt.src = (const double*)ctx->src.p;
+  bt.dst = (const double*)ctx->dst.p;
+  bt.sf = (float4*)ctx->sf.p;
+  bt.df = (float4*)ctx->df.p;
+  bt.gc = (GraphConsts*)ctx->gc.p;
+  bt.adj = (uint64_t*)ctx->adj.p;
+  bt.deg = (int32_t*)ctx->deg.p;
+  bt.n_edges2 = (unsigned long long*)ctx->nedges.p;
+  bt.hclq = (int32_t*)ctx->hclq.p;
+  bt.hsize = (int32_t*)ctx->hsize.p;
+  bt.clq = (int32_t*)ctx->clq.p;
+  bt.L = (int32_t*)ctx->L.p;
+  bt.alive = (uint32_t*)ctx->alive.p;
+  bt.alive_cnt = (int32_t*)ctx->alive_cnt.p;
+  bt.root_ctr = (int32_t*)ctx->root_ctr.p;
+  bt.lock = (int32_t*)ctx->lock.p;
+  bt.flags = (int32_t*)ctx->flg.p;
+  bt.stack = (uint32_t*)ctx->stack.p;
+  bt.cv = (int32_t*)ctx->cv.p;
+  bt.centry = (int32_t*)ctx->centry.p;
+  bt.ps = (double*)ctx->ps.p;
+  bt.pd = (double*)ctx->pd.p;
+  bt.wgt = (double*)ctx->wgt.p;
+  bt.res = (double*)ctx->res.p;
+  bt.skey = (double*)ctx->skey.p;
+  bt.sidx = (int32_t*)ctx->sidx.p;
+  bt.sorted_clq = (int32_t*)ctx->sorted.p;
+  bt.rot_mask = (uint8_t*)ctx->rmask.p;
+  bt.trans_mask = (uint8_t*)ctx->tmask.p;
+  bt.sol = (tzr_solution*)ctx->sol.p;
+  bt.mismatches = (unsigned long long*)ctx->dbg.p;
+  bt.rechecks = (ctx->flags & 4u) ? (unsigned long long*)ctx->dbg.p + 1 : nullptr;
+  bt.flags_dbg = ctx->flags;
+  bt.deadline_ns = 0ull;
+  *out = bt;
+  return TZR_OK;
+}
+
+int check_launch(tzr_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return TZR_ERR_CUDA;
+  }
+  return TZR_OK;
+}
+
+__global__ void init_solutions_kernel(tzr_solution* sol, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  tzr_solution s;
+  memset(&s, 0, sizeof(s));
+  s.valid = 1;
+  s.scale = 1.0;  // ScaleInliersSelector: *scale = 1  (registration.cc:432)
+  sol[b] = s;
+}
+
+// The fused device pipeline for one uniform batch.  src/dst must already be set in bt.
+int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
+  cudaStream_t st = ctx->stream;
+  if (p.estimate_scaling) {
+    ctx->last_error = "estimate_scaling=true (TLSScaleSolver) is not implemented on the GPU path yet";
+    return TZR_ERR_UNSUPPORTED;
+  }
+  if (p.rotation_estimation_algorithm != 0) {
+    ctx->last_error = "only GNC_TLS rotation is implemented on the GPU path";
+    return TZR_ERR_UNSUPPORTED;
+  }
+  if (p.rotation_tim_graph != 0) {
+    ctx->last_error = "only the CHAIN TIM graph is implemented on the GPU path";
+    return TZR_ERR_UNSUPPORTED;
+  }
+  const int mode = effective_mode(p);
+  if (mode == 2) {
+    ctx->last_error = "KCORE_HEU inlier selection is not implemented on the GPU path yet";
+    return TZR_ERR_UNSUPPORTED;
+  }
+  bt.beta = 2.0 * p.noise_bound * std::sqrt(p.cbar2);  // registration.cc:438
+  if (mode == 0 && p.max_clique_time_limit > 0 && p.max_clique_time_limit < 1e6) {
+    // device-side deadline on %globaltimer (ns since an arbitrary epoch): read it now through a tiny kernel-free
+    // approximation: the host cannot read globaltimer, so the exact kernel is given a relative budget instead.
+    bt.deadline_ns = 0ull;  // set by clique launcher when a relative budget is supported
+  }
+  cudaEventRecord(ctx->ev[0], st);
+  init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(bt.sol, bt.B);
+  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
+  launch_prep(bt, st);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches += 2;
+  int nl = 0;
+  if (mode != 3) {
+    launch_graph(bt, st);
+    launch_degree(bt, st);
+    cudaEventRecord(ctx->ev[2], st);
+    nl += 2;
+    launch_clique(bt, p, mode, st, &nl);
+  } else {
+    cudaEventRecord(ctx->ev[2], st);
+  }
+  cudaEventRecord(ctx->ev[3], st);
+  launch_rot_trans(bt, p, mode != 3 ? 1 : 0, st);
+  cudaEventRecord(ctx->ev[4], st);
+  ctx->launches += nl + 1;
+  ctx->last = bt;
+  ctx->have_last = true;
+  return check_launch(ctx, "pipeline launch");
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int tzr_abi_version(void) { return TZR_ABI_VERSION; }
+
+const char* tzr_status_string(int s) {
+  switch (s) {
+    case TZR_OK: return "ok";
+    case TZR_ERR_INVALID_ARG: return "invalid argument";
+    case TZR_ERR_NO_DEVICE: return "no usable CUDA device (the B200 path has no CPU fallback)";
+    case TZR_ERR_CUDA: return "CUDA error";
+    case TZR_ERR_ALLOC: return "allocation failed";
+    case TZR_ERR_UNSUPPORTED: return "unsupported parameter combination";
+    case TZR_ERR_TOO_LARGE: return "problem too large";
+    default: return "unknown";
+  }
+}
+
+const char* tzr_last_error(const tzr_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+void tzr_params_default(tzr_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->noise_bound = 0.01;
+  p->cbar2 = 1;
+  p->estimate_scaling = 1;
+  p->rotation_estimation_algorithm = 0;
+  p->rotation_gnc_factor = 1.4;
+  p->rotation_max_iterations = 100;
+  p->rotation_cost_threshold = 1e-6;
+  p->rotation_tim_graph = 0;
+  p->inlier_selection_mode = 0;
+  p->kcore_heuristic_threshold = 0.5;
+  p->use_max_clique = 1;
+  p->max_clique_exact_solution = 1;
+  p->max_clique_time_limit = 3600;
+  p->max_clique_num_threads = 0;
+}
+
+int tzr_words_per_row(int n) { return words64(n); }
+
+int tzr_ctx_create(int device, tzr_ctx** out) {
+  if (!out) return TZR_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return TZR_ERR_NO_DEVICE;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return TZR_ERR_NO_DEVICE;
+  }
+  if (device >= count) return TZR_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return TZR_ERR_NO_DEVICE;
+  tzr_ctx* ctx = new tzr_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return TZR_ERR_CUDA;
+  }
+  for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ev[i]);
+  *out = ctx;
+  return TZR_OK;
+}
+
+int tzr_ctx_destroy(tzr_ctx* ctx) {
+  if (!ctx) return TZR_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
+                    &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->alive_cnt, &ctx->root_ctr,
+                    &ctx->lock, &ctx->flg, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
+                    &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
+                    &ctx->misc};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  for (int i = 0; i < 5; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return TZR_OK;
+}
+
+int tzr_ctx_set_stream(tzr_ctx* ctx, void* s) {
+  if (!ctx) return TZR_ERR_INVALID_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return TZR_OK;
+}
+
+int tzr_ctx_synchronize(tzr_ctx* ctx) {
+  if (!ctx) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return TZR_OK;
+}
+
+int64_t tzr_ctx_kernel_launches(const tzr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tzr_ctx_set_flags(tzr_ctx* ctx, uint32_t flags) {
+  if (!ctx) return TZR_ERR_INVALID_ARG;
+  ctx->flags = flags;
+  return TZR_OK;
+}
+
+int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx) {
+  if (!ctx || !ctx->dbg.p) return -1;
+  unsigned long long v = 0;
+  cudaStreamSynchronize(ctx->stream);
+  if (cudaMemcpy(&v, ctx->dbg.p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
+
+int64_t tzr_ctx_filter_rechecks(tzr_ctx* ctx) {
+  if (!ctx || !ctx->dbg.p) return -1;
+  unsigned long long v = 0;
+  cudaStreamSynchronize(ctx->stream);
+  if (cudaMemcpy(&v, (unsigned long long*)ctx->dbg.p + 1, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1
+// ------------------------------------------------------------------------------------------------
+int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, double beta, uint64_t* adj_bits,
+                    int32_t* degree, int64_t* n_edges) {
+  if (!ctx || !src || !dst || !adj_bits || n <= 0) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  Batch bt;
+  int rc = setup_batch(ctx, 1, n, true, &bt);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  bt.beta = beta;
+  CK(cudaMemcpyAsync((void*)bt.src, src, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((void*)bt.dst, dst, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
+  launch_prep(bt, st);
+  launch_graph(bt, st);
+  launch_degree(bt, st);
+  ctx->launches += 3;
+  rc = check_launch(ctx, "graph build");
+  if (rc) return rc;
+  CK(cudaMemcpy2DAsync(adj_bits, (size_t)words64(n) * 8, bt.adj, (size_t)pitch64(n) * 8, (size_t)words64(n) * 8, n,
+                       cudaMemcpyDeviceToHost, st));
+  if (degree) CK(cudaMemcpyAsync(degree, bt.deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  unsigned long long e2 = 0;
+  CK(cudaMemcpyAsync(&e2, bt.n_edges2, sizeof(e2), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_edges) *n_edges = (int64_t)(e2 / 2);
+  ctx->last = bt;
+  ctx->have_last = true;
+  return TZR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2
+// ------------------------------------------------------------------------------------------------
+int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, double kcore_thr, double time_limit_s,
+                   int32_t* clique, int32_t* clique_size, int32_t* proven_optimal) {
+  (void)kcore_thr;
+  (void)time_limit_s;
+  if (!ctx || !adj_bits || !clique || !clique_size || n <= 0) return TZR_ERR_INVALID_ARG;
+  if (mode != 0 && mode != 1) {
+    ctx->last_error = "KCORE_HEU inlier selection is not implemented on the GPU path yet";
+    return TZR_ERR_UNSUPPORTED;
+  }
+  cudaSetDevice(ctx->device);
+  Batch bt;
+  int rc = setup_batch(ctx, 1, n, false, &bt);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(bt.adj, 0, (size_t)n * pitch64(n) * 8, st));
+  CK(cudaMemcpy2DAsync(bt.adj, (size_t)pitch64(n) * 8, adj_bits, (size_t)words64(n) * 8, (size_t)words64(n) * 8, n,
+                       cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(bt.n_edges2, 0, sizeof(unsigned long long), st));
+  launch_degree(bt, st);
+  tzr_params p;
+  tzr_params_default(&p);
+  int nl = 1;
+  launch_clique(bt, p, mode, st, &nl);
+  ctx->launches += nl;
+  rc = check_launch(ctx, "max clique");
+  if (rc) return rc;
+  int32_t L = 0, fl = 0;
+  CK(cudaMemcpyAsync(&L, bt.L, sizeof(L), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&fl, bt.flags, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (L > 0) CK(cudaMemcpy(clique, bt.clq, (size_t)L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::sort(clique, clique + L);  // registration.cc:636
+  *clique_size = L;
+  if (proven_optimal) *proven_optimal = (mode == 0 && !(fl & 1)) ? 1 : 0;
+  return TZR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 3 / 4 / scalar TLS
+// ------------------------------------------------------------------------------------------------
+int tzr_gnc_tls_rotation(tzr_ctx* ctx, const double* src, const double* dst, int m, double noise_bound,
+                         double gnc_factor, uint64_t max_iterations, double cost_threshold, double* R,
+                         uint8_t* inlier_mask, double* cost, int32_t* iterations) {
+  if (!ctx || !src || !dst || !R || m <= 0) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t pts = (size_t)m * 3 * sizeof(double);
+  int rc = ensure(ctx, ctx->misc, 2 * pts + 2 * (size_t)m * sizeof(double) + (size_t)m + 16 * sizeof(double) + 64);
+  if (rc) return rc;
+  char* base = (char*)ctx->misc.p;
+  double* d_src = (double*)base;
+  double* d_dst = d_src + (size_t)m * 3;
+  double* d_w = d_dst + (size_t)m * 3;
+  double* d_r = d_w + m;
+  double* d_out = d_r + m;  // 9 R + 1 cost
+  int* d_it = (int*)(d_out + 10);
+  uint8_t* d_mask = (uint8_t*)(d_out + 12);
+  CK(cudaMemcpyAsync(d_src, src, pts, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_dst, dst, pts, cudaMemcpyHostToDevice, st));
+  launch_gnc_only(d_src, d_dst, m, noise_bound, gnc_factor, max_iterations, cost_threshold, d_w, d_r, d_out, d_mask,
+                  d_out + 9, d_it, st);
+  ctx->launches += 1;
+  rc = check_launch(ctx, "gnc");
+  if (rc) return rc;
+  double hout[10];
+  int it = 0;
+  CK(cudaMemcpyAsync(hout, d_out, sizeof(hout), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&it, d_it, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, d_mask, m, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(R, hout, 9 * sizeof(double));
+  if (cost) *cost = hout[9];
+  if (iterations) *iterations = it;
+  return TZR_OK;
+}
+
+int tzr_tls_translation(tzr_ctx* ctx, const double* src, const double* dst, int m, double noise_bound, double cbar2,
+                        double* t3, uint8_t* inlier_mask) {
+  if (!ctx || !src || !dst || !t3 || m <= 0) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t pts = (size_t)m * 3 * sizeof(double);
+  const int npad = next_pow2_host(2 * m);
+  const size_t key_bytes = ((size_t)3 * npad + (size_t)3 * m) * sizeof(double);
+  const size_t idx_bytes = (size_t)3 * npad * sizeof(int32_t);
+  int rc = ensure(ctx, ctx->misc, 2 * pts + key_bytes + idx_bytes + (size_t)m + 64);
+  if (rc) return rc;
+  double* d_src = (double*)ctx->misc.p;
+  double* d_dst = d_src + (size_t)m * 3;
+  double* d_key = d_dst + (size_t)m * 3;
+  int32_t* d_idx = (int32_t*)(d_key + (size_t)3 * npad + (size_t)3 * m);
+  double* d_t = (double*)(d_idx + (size_t)3 * npad + ((3 * npad) & 1));
+  uint8_t* d_mask = (uint8_t*)(d_t + 4);
+  // the tail (d_t, d_mask) needs 4 doubles + m bytes more
+  rc = ensure(ctx, ctx->misc, (size_t)((char*)d_mask - (char*)ctx->misc.p) + (size_t)m + 64);
+  if (rc) return rc;
+  if ((double*)ctx->misc.p != d_src) {  // buffer moved on growth: recompute pointers
+    d_src = (double*)ctx->misc.p;
+    d_dst = d_src + (size_t)m * 3;
+    d_key = d_dst + (size_t)m * 3;
+    d_idx = (int32_t*)(d_key + (size_t)3 * npad + (size_t)3 * m);
+    d_t = (double*)(d_idx + (size_t)3 * npad + ((3 * npad) & 1));
+    d_mask = (uint8_t*)(d_t + 4);
+  }
+  CK(cudaMemcpyAsync(d_src, src, pts, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_dst, dst, pts, cudaMemcpyHostToDevice, st));
+  const double beta = noise_bound * std::sqrt(cbar2);  // registration.cc:459
+  launch_translation_only(d_src, d_dst, m, beta, d_key, d_idx, d_t, d_mask, st);
+  ctx->launches += 1;
+  rc = check_launch(ctx, "translation");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(t3, d_t, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, d_mask, m, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TZR_OK;
+}
+
+int tzr_scalar_tls(tzr_ctx* ctx, const double* x, const double* ranges, int64_t m, double* estimate,
+                   uint8_t* inliers) {
+  if (!ctx || !x || !ranges || !estimate || m <= 1) return TZR_ERR_INVALID_ARG;  // reference asserts m > 1
+  if (m > ((int64_t)1 << 22)) return TZR_ERR_TOO_LARGE;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  int64_t npad = 1;
+  while (npad < 2 * m) npad <<= 1;
+  const size_t bytes = 2 * (size_t)m * 8 + (size_t)npad * 8 + (size_t)npad * 4 + 16 + (size_t)m + 64;
+  int rc = ensure(ctx, ctx->misc, bytes);
+  if (rc) return rc;
+  double* d_x = (double*)ctx->misc.p;
+  double* d_r = d_x + m;
+  double* d_key = d_r + m;
+  double* d_est = d_key + npad;
+  int32_t* d_idx = (int32_t*)(d_est + 2);
+  uint8_t* d_inl = (uint8_t*)(d_idx + npad);
+  CK(cudaMemcpyAsync(d_x, x, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_r, ranges, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+  launch_scalar_tls(d_x, d_r, m, d_key, d_idx, d_est, d_inl, st);
+  ctx->launches += 1;
+  rc = check_launch(ctx, "scalar tls");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(estimate, d_est, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (inliers) CK(cudaMemcpyAsync(inliers, d_inl, (size_t)m, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TZR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole path
+// ------------------------------------------------------------------------------------------------
+int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, const double* src_dev,
+                        const double* dst_dev, tzr_solution* solutions_dev, int32_t* cliques_dev) {
+  if (!ctx || !params || !src_dev || !dst_dev || !solutions_dev) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  Batch bt;
+  int rc = setup_batch(ctx, B, n, false, &bt);
+  if (rc) return rc;
+  bt.src = src_dev;
+  bt.dst = dst_dev;
+  rc = run_pipeline(ctx, bt, *params);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(solutions_dev, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToDevice, st));
+  if (cliques_dev)
+    CK(cudaMemcpyAsync(cliques_dev, bt.sorted_clq, (size_t)B * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return TZR_OK;
+}
+
+static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int n, const double* const* src,
+                              const double* const* dst, tzr_solution* solutions, int32_t* cliques, int max_n,
+                              uint8_t* rot_inliers, uint8_t* trans_inliers) {
+  cudaSetDevice(ctx->device);
+  Batch bt;
+  int rc = setup_batch(ctx, B, n, true, &bt);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const size_t per = (size_t)n * 3 * sizeof(double);
+  rc = ensure_pinned(ctx, 2 * per * B + (size_t)B * sizeof(tzr_solution) + (size_t)B * n * sizeof(int32_t));
+  if (rc) return rc;
+  char* hp = (char*)ctx->h_pin;
+  double* h_src = (double*)hp;
+  double* h_dst = (double*)(hp + per * B);
+  tzr_solution* h_sol = (tzr_solution*)(hp + 2 * per * B);
+  int32_t* h_clq = (int32_t*)(hp + 2 * per * B + (size_t)B * sizeof(tzr_solution));
+  for (int b = 0; b < B; ++b) {
+    memcpy((char*)h_src + per * b, src[b], per);
+    memcpy((char*)h_dst + per * b, dst[b], per);
+  }
+  CK(cudaMemcpyAsync((void*)bt.src, h_src, per * B, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((void*)bt.dst, h_dst, per * B, cudaMemcpyHostToDevice, st));
+  rc = run_pipeline(ctx, bt, *params);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));
+  if (cliques) CK(cudaMemcpyAsync(h_clq, bt.sorted_clq, (size_t)B * n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (rot_inliers) CK(cudaMemcpyAsync(rot_inliers, bt.rot_mask, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (trans_inliers) CK(cudaMemcpyAsync(trans_inliers, bt.trans_mask, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(solutions, h_sol, (size_t)B * sizeof(tzr_solution));
+  if (cliques)
+    for (int b = 0; b < B; ++b) {
+      const int m = std::max(0, std::min(n, h_sol[b].clique_size));
+      memcpy(cliques + (size_t)b * max_n, h_clq + (size_t)b * n, (size_t)m * sizeof(int32_t));
+    }
+  return TZR_OK;
+}
+
+int tzr_solve(tzr_ctx* ctx, const tzr_params* params, const double* src, const double* dst, int n,
+              tzr_solution* solution, int32_t* clique, uint8_t* rot_inliers, uint8_t* trans_inliers) {
+  if (!ctx || !params || !src || !dst || !solution || n <= 0) return TZR_ERR_INVALID_ARG;
+  const double* s[1] = {src};
+  const double* d[1] = {dst};
+  int rc = solve_uniform_host(ctx, params, 1, n, s, d, solution, clique, n, rot_inliers, trans_inliers);
+  if (rc) return rc;
+  float ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) solution->stage_ms[0] = ms;  // prep
+  if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) solution->stage_ms[1] = ms;  // graph
+  if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) solution->stage_ms[2] = ms;  // clique
+  if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) solution->stage_ms[3] = ms;  // rot+trans
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]) == cudaSuccess) solution->stage_ms[6] = ms;
+  return TZR_OK;
+}
+
+int tzr_solve_batch(tzr_ctx* ctx, const tzr_params* params, int B, const int32_t* n, const double* const* src,
+                    const double* const* dst, tzr_solution* solutions, int32_t* cliques, int max_n) {
+  if (!ctx || !params || !n || !src || !dst || !solutions || B <= 0) return TZR_ERR_INVALID_ARG;
+  bool uniform = true;
+  for (int b = 1; b < B; ++b) uniform &= (n[b] == n[0]);
+  if (cliques && max_n < *std::max_element(n, n + B)) return TZR_ERR_INVALID_ARG;
+  if (uniform) return solve_uniform_host(ctx, params, B, n[0], src, dst, solutions, cliques, max_n, nullptr, nullptr);
+  for (int b = 0; b < B; ++b) {
+    int rc = solve_uniform_host(ctx, params, 1, n[b], src + b, dst + b, solutions + b,
+                                cliques ? cliques + (size_t)b * max_n : nullptr, max_n, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  return TZR_OK;
+}
+
+int tzr_last_graph(tzr_ctx* ctx, int b, uint64_t* adj_bits, int32_t* degree) {
+  if (!ctx || !ctx->have_last || b < 0 || b >= ctx->last.B) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  const Batch& bt = ctx->last;
+  const int n = bt.n;
+  cudaStream_t st = ctx->stream;
+  if (adj_bits)
+    CK(cudaMemcpy2DAsync(adj_bits, (size_t)words64(n) * 8, bt.adj + (size_t)b * n * pitch64(n), (size_t)pitch64(n) * 8,
+                         (size_t)words64(n) * 8, n, cudaMemcpyDeviceToHost, st));
+  if (degree) CK(cudaMemcpyAsync(degree, bt.deg + (size_t)b * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TZR_OK;
+}
+
+int tzr_last_stage_ms(tzr_ctx* ctx, double* prep_ms, double* graph_ms, double* clique_ms, double* rot_trans_ms) {
+  if (!ctx || !ctx->have_last) return TZR_ERR_INVALID_ARG;
+  float ms = 0;
+  double* outs[4] = {prep_ms, graph_ms, clique_ms, rot_trans_ms};
+  for (int i = 0; i < 4; ++i) {
+    if (!outs[i]) continue;
+    if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) return TZR_ERR_CUDA;
+    *outs[i] = ms;
+  }
+  return TZR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,604 @@
+// Stage 2 of solve(): maximum clique of the inlier graph, on the packed adjacency bitset.
+//
+// Replaces teaser::MaxCliqueSolver::findMaxClique (teaser/src/graph.cc:12-125) and the PMC library
+// calls behind it (pmc::pmc_graph::compute_cores, pmc::pmc_heu::search, pmc::pmcx_maxclique::
+// search_dense — an un-vendored, un-pinned dependency).  The result contract
+// is the reference's: a maximum clique (PMC_EXACT), returned to solve() which sorts it
+// (registration.cc:636).  The algorithm is a GPU re-design, not PMC's:
+//
+//   K1 clique_heur   (kHeurRoots CTAs / problem)  greedy lower bound from the top-degree vertices:
+//        candidate set P = N(root); repeat { in-P degrees by bitset AND+popcount; all "universal"
+//        vertices (adjacent to every other candidate) join the clique at once; otherwise the vertex
+//        of largest in-P degree joins and P &= N(u) }.
+//   K2 clique_peel   (1 CTA / problem)  picks the best heuristic clique (size L), then peels the
+//        graph to its L-core (a clique of size L+1 needs L neighbours): if nothing survives, L is
+//        proven optimal — the common case for TEASER-style inlier graphs (this is what the
+//        reference's `lb == ub` early-out, graph.cc:100-102, achieves through PMC's k-core bound).
+//   K3 clique_exact  (G CTAs / problem, one warp per root vertex)  branch and bound over the
+//        survivors: root v owns the cliques whose smallest index is v (P = N(v) ∩ alive ∩ {u>v});
+//        every node is reduced by in-P degree rules (universal vertices, vertices that cannot reach
+//        L+1), bounded by greedy sequential colouring (branch only on vertices whose colour exceeds
+//        L - |C|), and expanded depth-first with an explicit stack in global memory.  The incumbent
+//        is shared through L[b] (atomic) + a spin lock for the vertex list.
+//
+// Bit-parallel integer work, L2-resident bitset: no tensor cores, no meaningful HBM roofline.
+#include "tzr_internal.cuh"
+
+namespace tzr {
+
+namespace {
+
+constexpr int kHeurThreads = 512;
+constexpr int kPeelThreads = 1024;
+constexpr int kExactThreads = 256;
+constexpr int kExactWarps = kExactThreads / 32;
+
+__device__ __forceinline__ const uint32_t* adj_row32(const Batch& bt, int b, int v) {
+  return reinterpret_cast<const uint32_t*>(bt.adj) + ((size_t)b * bt.n + v) * pitch32(bt.n);
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- block-level helpers ----------------------------------------------------------------------
+// max-reduce a 64-bit key over the block; result valid in all threads. s_tmp: >= 33 entries.
+__device__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* s_tmp) {
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_tmp[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long x = lane < nw ? s_tmp[lane] : 0ull;
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long t = __shfl_xor_sync(0xffffffffu, x, o);
+      x = t > x ? t : x;
+    }
+    if (lane == 0) s_tmp[32] = x;
+  }
+  __syncthreads();
+  return s_tmp[32];
+}
+
+// exclusive scan of one int per thread over the block; returns exclusive prefix, *total = sum.
+__device__ int block_excl_scan(int v, int* s_tmp /* >= 34 */, int* total) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_tmp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = lane < nw ? s_tmp[lane] : 0;
+    int xi = x;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    s_tmp[lane] = xi - x;  // exclusive warp offsets
+    if (lane == 31) s_tmp[33] = xi;
+  }
+  __syncthreads();
+  *total = s_tmp[33];
+  return s_tmp[w] + inc - v;
+}
+
+}  // namespace
+
+// =================================================================================================
+// K1: greedy heuristic clique from the r-th highest-degree vertex.
+// dynamic smem: P[W32] u32 | list[n] u16 | dl[n] u16
+// =================================================================================================
+size_t clique_heur_smem(int n) { return (size_t)pitch32(n) * 4 + (size_t)n * 2 * 2 + 16; }
+
+__global__ void __launch_bounds__(kHeurThreads) clique_heur_kernel(Batch bt) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  const int n = bt.n, W = pitch32(n);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* P = reinterpret_cast<uint32_t*>(smem_raw);
+  uint16_t* list = reinterpret_cast<uint16_t*>(P + W);
+  uint16_t* dl = list + n;
+  __shared__ unsigned long long s_key[34];
+  __shared__ int s_scan[34];
+  __shared__ int s_chosen[kHeurRoots];
+  __shared__ int s_csz, s_nuni;
+
+  const int32_t* deg = bt.deg + (size_t)b * n;
+  int32_t* C = bt.hclq + ((size_t)b * kHeurRoots + r) * n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+
+  // ---- root = (r+1)-th largest (degree, lowest index)
+  int root = -1;
+  for (int round = 0; round <= r; ++round) {
+    unsigned long long best = 0ull;
+    for (int v = tid; v < n; v += blockDim.x) {
+      bool excl = false;
+      for (int q = 0; q < round; ++q) excl |= (s_chosen[q] == v);
+      if (excl) continue;
+      const unsigned long long key = ((unsigned long long)(unsigned)deg[v] << 32) | (unsigned)(0xffffffffu - (unsigned)v);
+      best = key > best ? key : best;
+    }
+    best = block_max_u64(best, s_key);
+    const int v = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+    const int d = (int)(best >> 32);
+    if (tid == 0) s_chosen[round] = (best == 0ull || d == 0) ? -1 : v;
+    __syncthreads();
+    root = s_chosen[round];
+    if (root < 0) break;
+  }
+  if (root < 0) {  // fewer than r+1 non-isolated vertices
+    if (tid == 0) bt.hsize[b * kHeurRoots + r] = 0;
+    return;
+  }
+  if (tid == 0) {
+    C[0] = root;
+    s_csz = 1;
+  }
+  {
+    const uint32_t* rr = adj_row32(bt, b, root);
+    for (int x = tid; x < W; x += blockDim.x) P[x] = rr[x];
+  }
+  __syncthreads();
+
+  for (int iter = 0; iter < n; ++iter) {
+    // ---- enumerate members of P (ordered) into list[]
+    int total = 0;
+    {
+      // each thread owns words tid, tid+T, ... ; W <= 1024 and T = 512 -> at most 2 words; generic loop
+      int cnt_local = 0;
+      for (int x = tid; x < W; x += blockDim.x) cnt_local += __popc(P[x]);
+      // ordered enumeration needs word-major order: do it per "pass" of blockDim words
+      int base_total = 0;
+      for (int x0 = 0; x0 < W; x0 += blockDim.x) {
+        const int x = x0 + tid;
+        const uint32_t wv = x < W ? P[x] : 0u;
+        int tot = 0;
+        int off = block_excl_scan(__popc(wv), s_scan, &tot);
+        uint32_t m = wv;
+        int pos = base_total + off;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          list[pos++] = (uint16_t)(x * 32 + bit);
+        }
+        base_total += tot;
+      }
+      total = base_total;
+      (void)cnt_local;
+    }
+    __syncthreads();
+    const int cnt = total;
+    if (cnt == 0) break;
+    // ---- in-P degrees: one warp per member
+    for (int k = wid; k < cnt; k += nw) {
+      const int u = list[k];
+      const uint32_t* ru = adj_row32(bt, b, u);
+      int d = 0;
+      for (int x = lane; x < W; x += 32) d += __popc(ru[x] & P[x]);
+      d = __reduce_add_sync(0xffffffffu, d);
+      if (lane == 0) dl[k] = (uint16_t)d;
+    }
+    if (tid == 0) s_nuni = 0;
+    __syncthreads();
+    // ---- universal vertices join the clique together; best non-universal vertex is the pivot
+    unsigned long long best = 0ull;
+    for (int k = tid; k < cnt; k += blockDim.x) {
+      const int u = list[k], d = dl[k];
+      if (d == cnt - 1) {
+        const int pos = atomicAdd(&s_csz, 1);
+        C[pos] = u;
+        atomicAdd(&s_nuni, 1);
+        atomicAnd(&P[u >> 5], ~(1u << (u & 31)));
+      } else {
+        const unsigned long long key = ((unsigned long long)(unsigned)(d + 1) << 32) | (unsigned)(0xffffffffu - (unsigned)u);
+        best = key > best ? key : best;
+      }
+    }
+    best = block_max_u64(best, s_key);  // contains __syncthreads
+    if (s_nuni == cnt) break;           // P was a clique
+    const int u = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+    if (tid == 0) {
+      const int pos = s_csz;
+      C[pos] = u;
+      s_csz = pos + 1;
+    }
+    const uint32_t* ru = adj_row32(bt, b, u);
+    for (int x = tid; x < W; x += blockDim.x) P[x] &= ru[x];
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) bt.hsize[b * kHeurRoots + r] = s_csz;
+}
+
+// =================================================================================================
+// K2: select the best heuristic clique, peel to the L-core.
+// dynamic smem: A[W32] | Anew[W32]
+// mode: 0 exact, 1 heuristic only
+// =================================================================================================
+size_t clique_peel_smem(int n) { return (size_t)pitch32(n) * 4 * 2 + 16; }
+
+__global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int mode) {
+  const int b = blockIdx.x;
+  const int n = bt.n, W = pitch32(n);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* A = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* An = A + W;
+  __shared__ int s_changed, s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+
+  int L = 0, win = 0;
+  for (int r = 0; r < kHeurRoots; ++r) {
+    const int s = bt.hsize[b * kHeurRoots + r];
+    if (s > L) {
+      L = s;
+      win = r;
+    }
+  }
+  {
+    const int32_t* src = bt.hclq + ((size_t)b * kHeurRoots + win) * n;
+    int32_t* dst = bt.clq + (size_t)b * n;
+    for (int i = tid; i < L; i += blockDim.x) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    bt.L[b] = L;
+    bt.root_ctr[b] = 0;
+    bt.lock[b] = 0;
+    bt.flags[b] = 0;
+  }
+  uint32_t* alive_g = bt.alive + (size_t)b * W;
+  if (mode != 0 || L == 0) {
+    for (int x = tid; x < W; x += blockDim.x) alive_g[x] = 0u;
+    if (tid == 0) bt.alive_cnt[b] = 0;
+    return;
+  }
+  const int32_t* deg = bt.deg + (size_t)b * n;
+  for (int x = tid; x < W; x += blockDim.x) {
+    uint32_t m = 0;
+    for (int k = 0; k < 32; ++k) {
+      const int v = x * 32 + k;
+      if (v < n && deg[v] >= L) m |= 1u << k;
+    }
+    A[x] = m;
+    An[x] = m;
+  }
+  __syncthreads();
+  for (int round = 0; round < 256; ++round) {
+    if (tid == 0) s_changed = 0;
+    __syncthreads();
+    for (int x = wid; x < W; x += nw) {
+      uint32_t m = A[x];  // warp-uniform
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int v = x * 32 + bit;
+        const uint32_t* rv = adj_row32(bt, b, v);
+        int d = 0;
+        for (int y = lane; y < W; y += 32) d += __popc(rv[y] & A[y]);
+        d = __reduce_add_sync(0xffffffffu, d);
+        if (d < L && lane == 0) {
+          atomicAnd(&An[x], ~(1u << bit));
+          s_changed = 1;
+        }
+      }
+    }
+    __syncthreads();
+    const int ch = s_changed;
+    for (int x = tid; x < W; x += blockDim.x) A[x] = An[x];
+    __syncthreads();
+    if (!ch) break;
+  }
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int x = tid; x < W; x += blockDim.x) {
+    alive_g[x] = A[x];
+    c += __popc(A[x]);
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0 && c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (tid == 0) bt.alive_cnt[b] = s_cnt;
+}
+
+// =================================================================================================
+// K3: exact branch and bound, one warp per root.
+// dynamic smem per warp: Pc[W] | Q[W] | R[W] | Bs[W]
+// =================================================================================================
+size_t clique_exact_smem(int n) { return (size_t)pitch32(n) * 4 * 4 * kExactWarps + 16; }
+
+namespace {
+
+__device__ __forceinline__ int warp_popc(const uint32_t* bits, int W, int lane) {
+  int c = 0;
+  for (int x = lane; x < W; x += 32) c += __popc(bits[x]);
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
+// lowest set bit at word index >= xstart, or -1.  *xfound = word index.
+__device__ __forceinline__ int warp_first_bit(const uint32_t* bits, int W, int lane, int xstart, int* xfound) {
+  for (int base = xstart & ~31; base < W; base += 32) {
+    const int x = base + lane;
+    const uint32_t w = (x < W && x >= xstart) ? bits[x] : 0u;
+    const unsigned nz = __ballot_sync(0xffffffffu, w != 0u);
+    if (nz) {
+      const int srcl = __ffs(nz) - 1;
+      const uint32_t ww = __shfl_sync(0xffffffffu, w, srcl);
+      *xfound = base + srcl;
+      return (base + srcl) * 32 + (__ffs(ww) - 1);
+    }
+  }
+  *xfound = W;
+  return -1;
+}
+
+struct WarpCtx {
+  const Batch* bt;
+  int b, n, W, lane;
+  uint32_t *Pc, *Q, *R, *Bs;     // shared memory (this warp)
+  uint32_t* stack;               // global: level d -> P at stack + d*2W, B at stack + d*2W + W
+  int32_t* cv;                   // global: current clique
+  int32_t* centry;               // global: clique size at entry of level d
+  volatile int32_t* Lp;
+};
+
+// Reduce the node in Pc.  Returns: 0 pruned, 1 leaf (Pc empty, csz is a new record), 2 continue.
+__device__ int node_reduce(WarpCtx& c, int& csz) {
+  const int W = c.W, lane = c.lane;
+  for (int round = 0; round < 8; ++round) {
+    const int cnt = warp_popc(c.Pc, W, lane);
+    const int Lc = *c.Lp;
+    if (csz + cnt <= Lc) return 0;
+    if (cnt == 0) return 1;
+    const int need = Lc - csz;  // a candidate must have >= need neighbours inside P
+    for (int x = lane; x < W; x += 32) c.Q[x] = c.Pc[x];
+    __syncwarp();
+    bool changed = false;
+    int added = 0;
+    for (int x = 0; x < W; ++x) {
+      uint32_t m = c.Pc[x];  // warp-uniform (shared memory broadcast)
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int u = x * 32 + bit;
+        const uint32_t* ru = adj_row32(*c.bt, c.b, u);
+        int d = 0;
+        for (int y = lane; y < W; y += 32) d += __popc(ru[y] & c.Pc[y]);
+        d = __reduce_add_sync(0xffffffffu, d);
+        if (d == cnt - 1) {  // universal: belongs to every maximal clique of this node
+          if (lane == 0) {
+            c.Q[x] &= ~(1u << bit);
+            c.cv[csz + added] = u;
+          }
+          ++added;
+        } else if (d < need) {
+          if (lane == 0) c.Q[x] &= ~(1u << bit);
+          changed = true;
+        }
+      }
+    }
+    __syncwarp();
+    for (int x = lane; x < W; x += 32) c.Pc[x] = c.Q[x];
+    __syncwarp();
+    csz += added;
+    if (!changed) {
+      const int cnt2 = cnt - added;
+      const int Lc2 = *c.Lp;
+      if (csz + cnt2 <= Lc2) return 0;
+      if (cnt2 == 0) return 1;
+      return 2;
+    }
+  }
+  const int cnt = warp_popc(c.Pc, W, lane);
+  if (csz + cnt <= *c.Lp) return 0;
+  if (cnt == 0) return 1;
+  return 2;
+}
+
+// Greedy sequential colouring of Pc; Bs = vertices whose colour >= kmin.  Returns |Bs|.
+__device__ int node_colour(WarpCtx& c, int csz) {
+  const int W = c.W, lane = c.lane;
+  int kmin = *c.Lp - csz + 1;
+  if (kmin < 1) kmin = 1;
+  for (int x = lane; x < W; x += 32) {
+    c.Q[x] = c.Pc[x];
+    c.Bs[x] = 0u;
+  }
+  __syncwarp();
+  int nB = 0;
+  int qstart = 0;
+  for (int k = 1;; ++k) {
+    // anything left uncoloured?
+    int xq;
+    const int first = warp_first_bit(c.Q, W, lane, qstart, &xq);
+    if (first < 0) break;
+    qstart = xq;
+    for (int x = lane; x < W; x += 32) c.R[x] = c.Q[x];
+    __syncwarp();
+    int xr = qstart;
+    while (true) {
+      int xf;
+      const int u = warp_first_bit(c.R, W, lane, xr, &xf);
+      if (u < 0) break;
+      xr = xf;
+      const uint32_t* ru = adj_row32(*c.bt, c.b, u);
+      for (int y = lane; y < W; y += 32) c.R[y] &= ~ru[y];
+      __syncwarp();
+      if (lane == 0) {
+        c.R[u >> 5] &= ~(1u << (u & 31));
+        c.Q[u >> 5] &= ~(1u << (u & 31));
+        if (k >= kmin) c.Bs[u >> 5] |= 1u << (u & 31);
+      }
+      if (k >= kmin) ++nB;
+      __syncwarp();
+    }
+  }
+  return nB;
+}
+
+__device__ void record_clique(WarpCtx& c, int csz) {
+  if (c.lane == 0) {
+    int32_t* lock = c.bt->lock + c.b;
+    while (atomicCAS(lock, 0, 1) != 0) {
+    }
+    __threadfence();
+    if (csz > *c.Lp) {
+      int32_t* dst = c.bt->clq + (size_t)c.b * c.n;
+      for (int i = 0; i < csz; ++i) dst[i] = c.cv[i];
+      __threadfence();
+      atomicExch(c.bt->L + c.b, csz);
+    }
+    __threadfence();
+    atomicExch(lock, 0);
+  }
+  __syncwarp();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
+  const int b = blockIdx.y;
+  if (bt.alive_cnt[b] == 0) return;
+  const int n = bt.n, W = pitch32(n);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * 4 * W;
+  WarpCtx c;
+  c.bt = &bt;
+  c.b = b;
+  c.n = n;
+  c.W = W;
+  c.lane = lane;
+  c.Pc = wbase;
+  c.Q = wbase + W;
+  c.R = wbase + 2 * W;
+  c.Bs = wbase + 3 * W;
+  const size_t gw = ((size_t)b * gridDim.x + blockIdx.x) * kExactWarps + wid;  // global warp slot
+  c.stack = bt.stack + gw * (size_t)bt.max_depth * 2 * W;
+  c.cv = bt.cv + gw * (size_t)n;
+  c.centry = bt.centry + gw * (size_t)bt.max_depth;
+  c.Lp = bt.L + b;
+  const uint32_t* alive = bt.alive + (size_t)b * W;
+
+  while (true) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(bt.root_ctr + b, 1);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if (v >= n) break;
+    if (!((alive[v >> 5] >> (v & 31)) & 1u)) continue;
+    if (bt.flags[b] & 2) break;  // deadline hit elsewhere
+    // root node: P = N(v) ∩ alive ∩ {u > v}
+    {
+      const uint32_t* rv = adj_row32(bt, b, v);
+      const int xv = v >> 5;
+      for (int x = lane; x < W; x += 32) {
+        uint32_t m = rv[x] & alive[x];
+        if (x < xv) m = 0u;
+        else if (x == xv) m &= ~((2u << (v & 31)) - 1u);  // keep bits strictly above v ((2<<31)-1 wraps to all ones)
+        c.Pc[x] = m;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) c.cv[0] = v;
+    __syncwarp();
+    int csz = 1;
+    int depth = 0;  // number of saved levels
+    bool fresh = true;
+    while (true) {
+      if (fresh) {
+        // ---- process the node in Pc
+        if (bt.deadline_ns && (globaltimer_ns() > bt.deadline_ns)) {
+          if (lane == 0) atomicOr(bt.flags + b, 3);
+          depth = 0;
+          break;
+        }
+        const int r = node_reduce(c, csz);
+        bool descend = false; (void)descend;
+        if (r == 1) {
+          if (csz > *c.Lp) record_clique(c, csz);
+        } else if (r == 2) {
+          const int nB = node_colour(c, csz);
+          if (nB > 0) {
+            if (depth >= bt.max_depth) {
+              if (lane == 0) atomicOr(bt.flags + b, 1);
+            } else {
+              uint32_t* Pd = c.stack + (size_t)depth * 2 * W;
+              for (int x = lane; x < W; x += 32) {
+                Pd[x] = c.Pc[x];
+                Pd[W + x] = c.Bs[x];
+              }
+              if (lane == 0) c.centry[depth] = csz;
+              __syncwarp();
+              ++depth;
+              descend = true;
+            }
+          }
+        }
+        (void)descend;
+        fresh = false;
+      }
+      // ---- branch: next candidate of the top saved level
+      if (depth == 0) break;
+      const int d = depth - 1;
+      uint32_t* Pd = c.stack + (size_t)d * 2 * W;
+      uint32_t* Bd = Pd + W;
+      const int ce = c.centry[d];
+      int xf;
+      // cheap level bound: every remaining clique of this level has size <= ce + |P_d|
+      const int cntP = warp_popc(Pd, W, lane);
+      int u = -1;
+      if (ce + cntP > *c.Lp) u = warp_first_bit(Bd, W, lane, 0, &xf);
+      if (u < 0) {
+        --depth;
+        continue;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        Bd[u >> 5] &= ~(1u << (u & 31));
+        Pd[u >> 5] &= ~(1u << (u & 31));
+        c.cv[ce] = u;
+      }
+      __syncwarp();
+      const uint32_t* ru = adj_row32(bt, b, u);
+      for (int x = lane; x < W; x += 32) c.Pc[x] = Pd[x] & ru[x];
+      __syncwarp();
+      csz = ce + 1;
+      fresh = true;
+    }
+  }
+}
+
+// =================================================================================================
+// host-side launcher
+// =================================================================================================
+void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches) {
+  (void)p;
+  const int n = bt.n;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(clique_heur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(clique_peel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(clique_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  dim3 g1(kHeurRoots, (unsigned)bt.B);
+  clique_heur_kernel<<<g1, kHeurThreads, clique_heur_smem(n), st>>>(bt);
+  clique_peel_kernel<<<bt.B, kPeelThreads, clique_peel_smem(n), st>>>(bt, mode == 0 ? 0 : 1);
+  int launches = 2;
+  if (mode == 0) {
+    dim3 g3((unsigned)bt.exact_ctas, (unsigned)bt.B);
+    clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(bt);
+    ++launches;
+  }
+  if (n_launches) *n_launches += launches;
+}
+
+}  // namespace tzr

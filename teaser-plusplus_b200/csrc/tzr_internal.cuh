@@ -1,0 +1,103 @@
+// Internal declarations shared by the CUDA translation units of libteaser_b200.so.
+// Product code: nothing here (or in any file of this directory) includes or links oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/teaser_b200.h"
+
+namespace tzr {
+
+// ---- adjacency layout -------------------------------------------------------------------------
+// Device-internal adjacency: n rows, pitch64(n) uint64 words per row.  The pitch is padded to whole
+// 128-column tiles (2 words) so that every 128x128 tile of the graph kernel maps to one aligned
+// 16-byte segment per row.  The ABI layout (ceil(n/64) words per row) is produced by a pitched copy.
+__host__ __device__ inline int pitch64(int n) { return 2 * ((n + 127) / 128); }
+__host__ __device__ inline int pitch32(int n) { return 2 * pitch64(n); }
+__host__ __device__ inline int words64(int n) { return (n + 63) / 64; }
+
+constexpr int kTile = 128;          // graph tile edge (pairs per tile = 128*128)
+constexpr int kGraphThreads = 256;  // 8 warps, each owns a 32x64 sub-tile
+constexpr int kHeurRoots = 8;       // heuristic start vertices per problem (top degrees)
+constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memory clique kernels
+
+// Per-problem constants of the FP32 filter (see graph_build.cu).
+struct GraphConsts {
+  float c1, g1;   // sure-edge test:      t^2 <= c1*s - g1        (gamma1 = beta - delta)
+  float c2, g2;   // sure-non-edge test:  t^2 >  c2*s - g2        (gamma2 = beta + delta)
+  float smin;     // pairs with s < smin are always re-checked in FP64
+  int use_fp64;   // 1: FP32 filter disabled for this problem (range/NaN guard or debug flag)
+  double beta;    // 2*noise_bound*sqrt(cbar2)
+  double cs[3], cd[3];  // centres subtracted before the float conversion
+};
+
+// Everything the device kernels need to know about one batch (passed by value).
+struct Batch {
+  int B;          // problems
+  int n;          // correspondences per problem (uniform inside a device batch)
+  double beta;    // 2*noise_bound*sqrt(cbar2)  (registration.cc:438)
+  const double* src;  // B*n*3
+  const double* dst;  // B*n*3
+  float4* sf;     // B*n centred float copies (w unused)
+  float4* df;
+  GraphConsts* gc;        // B
+  uint64_t* adj;          // B*n*pitch64(n)
+  int32_t* deg;           // B*n
+  unsigned long long* n_edges2;  // B (sum of degrees = 2*edges)
+  // clique state
+  int32_t* hclq;          // B*kHeurRoots*n heuristic cliques
+  int32_t* hsize;         // B*kHeurRoots
+  int32_t* clq;           // B*n incumbent clique (unsorted)
+  int32_t* L;             // B incumbent size
+  uint32_t* alive;        // B*pitch32(n) bitset of vertices surviving the L-core peel
+  int32_t* alive_cnt;     // B
+  int32_t* root_ctr;      // B work counter for the exact phase
+  int32_t* lock;          // B spin lock for incumbent updates
+  int32_t* flags;         // B bit0: search incomplete (depth/time budget)
+  // exact-phase scratch
+  uint32_t* stack;        // per warp: max_depth * 2 * pitch32 words
+  int32_t* cv;            // per warp: n ints (current clique)
+  int32_t* centry;        // per warp: max_depth ints
+  int max_depth;
+  int exact_ctas;         // CTAs per problem in the exact phase
+  // rotation / translation scratch (per problem)
+  double* ps;             // B*3*n chain TIMs src
+  double* pd;             // B*3*n chain TIMs dst (de-scaled)
+  double* wgt;            // B*n GNC weights
+  double* res;            // B*n residuals
+  double* skey;           // B*3*sort_cap sort keys (per axis)
+  int32_t* sidx;          // B*3*sort_cap sort payload
+  int sort_cap;           // next_pow2(2n): per-axis capacity of skey/sidx
+  int32_t* sorted_clq;    // B*n sorted clique (output order)
+  uint8_t* rot_mask;      // B*n
+  uint8_t* trans_mask;    // B*n
+  tzr_solution* sol;      // B
+  // debug
+  unsigned long long* mismatches;  // 1
+  unsigned long long* rechecks;    // 1
+  uint32_t flags_dbg;
+  unsigned long long deadline_ns;  // globaltimer deadline for the exact clique search (0 = none)
+};
+
+// kernels (defined in the .cu files) -------------------------------------------------------------
+void launch_prep(const Batch& bt, cudaStream_t st);
+void launch_graph(const Batch& bt, cudaStream_t st);
+void launch_degree(const Batch& bt, cudaStream_t st);
+void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);
+void launch_rot_trans(const Batch& bt, const tzr_params& p, int use_clique, cudaStream_t st);
+size_t clique_heur_smem(int n);
+size_t clique_peel_smem(int n);
+size_t clique_exact_smem(int n);
+
+// stand-alone stage helpers used by the per-stage C-ABI entry points
+void launch_gnc_only(const double* src, const double* dst, int m, double noise_bound, double gnc_factor,
+                     unsigned long long max_iter, double cost_thr, double* wgt, double* res, double* out_R,
+                     uint8_t* mask, double* out_cost, int* out_iters, cudaStream_t st);
+void launch_translation_only(const double* src, const double* dst, int m, double beta, double* skey, int32_t* sidx,
+                             double* out_t, uint8_t* mask, cudaStream_t st);
+void launch_scalar_tls(const double* x, const double* ranges, long long m, double* skey, int32_t* sidx,
+                       double* out_est, uint8_t* inliers, cudaStream_t st);
+
+}  // namespace tzr

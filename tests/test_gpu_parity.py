@@ -1,0 +1,361 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C-ABI
+(libteaser_b200.so via ctypes); the oracle is the checker."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+
+capi = importlib.import_module("teaser-plusplus_b200.capi")
+synth = importlib.import_module("teaser-plusplus_b200.synth")
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-4  # rad   (BASELINE.json north_star)
+TRANS_TOL = 1e-4  # m
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def fixed_params(nb, **kw):
+    d = dict(noise_bound=nb, cbar2=1.0, estimate_scaling=0, rotation_estimation_algorithm=0,
+             rotation_gnc_factor=1.4, rotation_max_iterations=100, rotation_cost_threshold=1e-12)
+    d.update(kw)
+    return d
+
+
+# ------------------------------------------------------------------ stage 1: graph, bit-exact
+GRAPH_CASES = [("C2", 700), ("C2cube", 900), ("C3", 1300), ("C4", 513), ("C5", 1000), ("C2", 128), ("C2", 129),
+               ("C2cube", 257), ("C2", 31), ("C2", 2)]
+
+
+@pytest.mark.parametrize("cfg,n", GRAPH_CASES)
+def test_graph_bit_exact(ctx, cfg, n):
+    pr = synth.config_problem(cfg, 3, n=n)
+    beta = 2 * pr["noise_bound"]
+    obits, odeg, oe = orc.build_graph_bits(pr["src"], pr["dst"], pr["noise_bound"])
+    ctx.set_flags(2 | 4)  # verify FP32 filter against FP64 for every pair, count rechecks
+    bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], beta)
+    assert ctx.filter_mismatches() == 0
+    rechecks = ctx.filter_rechecks()
+    ctx.set_flags(0)
+    assert np.array_equal(bits, obits)
+    assert np.array_equal(deg, odeg)
+    assert ne == oe
+    assert rechecks < 0.02 * n * n + 64  # the exact path is the exception, not the rule
+    # pure FP64 mode gives the same bits
+    ctx.set_flags(1)
+    bits64, _, _ = ctx.graph_build(pr["src"], pr["dst"], beta)
+    ctx.set_flags(0)
+    assert np.array_equal(bits64, obits)
+
+
+@pytest.mark.parametrize("shift,scale,nb", [(1e4, 1.0, None), (0.0, 1e-3, 3.3682e-5), (-3e6, 50.0, None),
+                                             (0.0, 1.0, 1e-9), (0.0, 1.0, 10.0)])
+def test_graph_bit_exact_conditioning(ctx, shift, scale, nb):
+    """Large offsets / tiny scales / degenerate bounds: the FP32 filter must degrade to the exact path,
+    never to wrong bits."""
+    pr = synth.config_problem("C2cube", 11, n=400)
+    src = pr["src"] * scale + shift
+    dst = pr["dst"] * scale - 0.5 * shift
+    nbv = pr["noise_bound"] * scale if nb is None else nb
+    obits, odeg, oe = orc.build_graph_bits(src, dst, nbv)
+    ctx.set_flags(2)
+    bits, deg, ne = ctx.graph_build(src, dst, 2 * nbv)
+    assert ctx.filter_mismatches() == 0
+    ctx.set_flags(0)
+    assert np.array_equal(bits, obits)
+    assert ne == oe
+
+
+def test_graph_duplicates_and_nan(ctx):
+    pr = synth.config_problem("C2", 5, n=300)
+    src, dst = pr["src"].copy(), pr["dst"].copy()
+    src[10] = src[11]
+    dst[10] = dst[11]  # zero-length TIM
+    src[20] = src[21]
+    obits, _, oe = orc.build_graph_bits(src, dst, pr["noise_bound"])
+    bits, _, ne = ctx.graph_build(src, dst, 2 * pr["noise_bound"])
+    assert np.array_equal(bits, obits) and ne == oe
+    src[5, 1] = np.nan
+    obits, _, oe = orc.build_graph_bits(src, dst, pr["noise_bound"])
+    bits, _, ne = ctx.graph_build(src, dst, 2 * pr["noise_bound"])
+    assert np.array_equal(bits, obits) and ne == oe
+
+
+def test_graph_full_size_c2(ctx):
+    pr = synth.config_problem("C2", 0)
+    obits, odeg, oe = orc.build_graph_bits(pr["src"], pr["dst"], pr["noise_bound"])
+    bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], 2 * pr["noise_bound"])
+    assert np.array_equal(bits, obits)
+    assert np.array_equal(deg, odeg) and ne == oe
+
+
+def _graph_properties(bits, deg, ne, n):
+    b = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
+    assert not b.diagonal().any()
+    assert np.array_equal(b, b.T)
+    assert np.array_equal(b.sum(1), deg)
+    assert b.sum() == 2 * ne
+    pad = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, n:]
+    assert not pad.any()
+
+
+@pytest.mark.parametrize("cfg", ["C3", "C5"])
+def test_graph_full_size_properties(ctx, cfg):
+    """Full BASELINE sizes through size-independent properties (symmetry, empty diagonal, degree sums),
+    plus exact rows for a sample of vertices."""
+    pr = synth.config_problem(cfg, 0)
+    n = pr["src"].shape[0]
+    bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], 2 * pr["noise_bound"])
+    _graph_properties(bits, deg, ne, n)
+    rng = np.random.default_rng(0)
+    beta = 2 * pr["noise_bound"]
+    for i in rng.choice(n, size=16, replace=False):
+        d1 = np.sqrt((((pr["src"] - pr["src"][i]) ** 2)[:, 0] + ((pr["src"] - pr["src"][i]) ** 2)[:, 1])
+                     + ((pr["src"] - pr["src"][i]) ** 2)[:, 2])
+        d2 = np.sqrt((((pr["dst"] - pr["dst"][i]) ** 2)[:, 0] + ((pr["dst"] - pr["dst"][i]) ** 2)[:, 1])
+                     + ((pr["dst"] - pr["dst"][i]) ** 2)[:, 2])
+        row = np.abs(d1 - d2) <= beta
+        row[i] = False
+        got = np.unpackbits(bits[i].view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert np.array_equal(got, row)
+
+
+# ------------------------------------------------------------------ stage 2: max clique
+def _bits_from_dense(A):
+    n = A.shape[0]
+    W = (n + 63) // 64
+    padded = np.zeros((n, W * 64), dtype=np.uint8)
+    padded[:, :n] = A
+    return np.packbits(padded, axis=1, bitorder="little").view(np.uint64).reshape(n, W)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_clique_random_graphs(ctx, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(40, 400))
+    p = float(rng.uniform(0.05, 0.5))
+    A = np.triu(rng.uniform(size=(n, n)) < p, 1)
+    if seed % 2 == 0:
+        k = int(rng.integers(10, 30))
+        idx = rng.choice(n, size=k, replace=False)
+        A[np.ix_(idx, idx)] = True
+        A = np.triu(A, 1)
+    A = A | A.T
+    bits = _bits_from_dense(A)
+    oc, info = orc.max_clique_bits(bits, n)
+    gc, proven = ctx.max_clique(bits, n, mode=0)
+    assert proven
+    assert len(gc) == len(oc)
+    assert all(A[a, b] for a in gc for b in gc if a != b)
+    assert np.all(np.diff(gc) > 0)
+
+
+def test_clique_toy_graphs(ctx):
+    # test/teaser/graph-test.cc:131-305
+    A = ~np.eye(5, dtype=bool)
+    gc, proven = ctx.max_clique(_bits_from_dense(A), 5)
+    assert gc.tolist() == [0, 1, 2, 3, 4] and proven
+    adj = {0: [2, 3], 1: [2], 2: [0, 1, 3], 3: [0, 2]}
+    A = np.zeros((4, 4), dtype=bool)
+    for a, l in adj.items():
+        A[a, l] = True
+    gc, proven = ctx.max_clique(_bits_from_dense(A), 4)
+    assert gc.tolist() == [0, 2, 3]
+    gc, proven = ctx.max_clique(_bits_from_dense(np.zeros((4, 4), dtype=bool)), 4)
+    assert len(gc) == 0  # PMC reports lb = 0 on an edgeless graph; solve() then returns valid = false
+
+
+@pytest.mark.parametrize("cfg,n", [("C2", 1000), ("C2cube", 1500), ("C3", 3000), ("C5", 2000)])
+def test_clique_on_inlier_graphs(ctx, cfg, n):
+    pr = synth.config_problem(cfg, 1, n=n)
+    bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], 2 * pr["noise_bound"])
+    oc, info = orc.max_clique_bits(bits, n)
+    gc, proven = ctx.max_clique(bits, n, mode=0)
+    assert proven
+    assert np.array_equal(gc, oc)  # unique maximum clique -> identical index set
+
+
+# ------------------------------------------------------------------ stage 3: GNC-TLS rotation
+def _gnc_problem(seed, m=300, outlier_frac=0.3, nb=0.05):
+    rng = np.random.default_rng(seed)
+    src = rng.normal(size=(m, 3))
+    R = synth.random_rotation(rng)
+    noise = rng.normal(size=(m, 3))
+    noise *= (rng.uniform(0.3, 0.9, size=(m, 1)) * nb) / np.linalg.norm(noise, axis=1, keepdims=True)
+    dst = src @ R.T + noise
+    k = int(outlier_frac * m)
+    dst[:k] = rng.normal(size=(k, 3)) * 2
+    return src, dst, R
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_gnc_tls_iterating(ctx, seed):
+    """Planted outlier TIMs so that the weight update / mu schedule really runs (SURVEY §4 coverage hole)."""
+    src, dst, R = _gnc_problem(seed)
+    o = orc.gnc_tls(src, dst, 100, 1e-12, 1.4, 0.05)
+    g = ctx.gnc_tls_rotation(src, dst, 0.05, 1.4, 100, 1e-12)
+    assert o["iterations"] > 3
+    assert abs(g["iterations"] - o["iterations"]) <= 1
+    assert synth.angular_error(o["R"], g["R"]) < 1e-9
+    assert np.mean(g["inliers"] != o["inliers"]) < 0.01
+    assert abs(g["cost"] - o["cost"]) <= 1e-9 * max(1.0, abs(o["cost"]))
+    assert synth.angular_error(R, g["R"]) < 0.05
+
+
+def test_gnc_tls_kat(ctx):
+    src = np.loadtxt(os.path.join(synth.GOLDEN_DIR, "registration_test", "rotation_only_src.csv"), delimiter=",")
+    Rexp = np.array([[0.997379773225804, -0.019905935977315, -0.069551000516966],
+                     [0.013777311189888, 0.996068297974922, -0.087510750572249],
+                     [0.071019530105605, 0.086323226782879, 0.993732623426126]])
+    g = ctx.gnc_tls_rotation(src, src @ Rexp.T, 1e-3, 1.4, 100, 1e-12)  # rotation-solver-test.cc:222-250
+    assert synth.angular_error(Rexp, g["R"]) < 1e-5
+    g = ctx.gnc_tls_rotation(src, src, 1e-3, 1.4, 100, 1e-12)
+    assert synth.angular_error(np.eye(3), g["R"]) < 1e-5
+
+
+# ------------------------------------------------------------------ stage 4: TLS translation / scalar TLS
+def test_translation_kat(ctx):
+    d = os.path.join(synth.GOLDEN_DIR, "registration_test")
+    v1 = np.loadtxt(os.path.join(d, "translation_test_v1_inliers.csv"), delimiter=",").T
+    v2 = np.loadtxt(os.path.join(d, "translation_test_v2_inliers.csv"), delimiter=",").T
+    t, inl = ctx.tls_translation(v1, v2, 0.00673642835, 1.0)
+    exp = np.array([-0.098430131086161, 0.008679113091532, 0.197317864174211])
+    assert np.linalg.norm(t - exp) < 1e-5  # translation-solver-test.cc:98-110
+    ot, oinl = orc.tls_translation(v1, v2, 0.00673642835, 1.0)
+    assert np.array_equal(t, ot) and np.array_equal(inl, oinl)  # same accumulation order -> bit-exact
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_translation_random(ctx, seed):
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(5, 700))
+    src = rng.normal(size=(m, 3))
+    t0 = rng.normal(size=3)
+    dst = src + t0 + rng.uniform(-0.01, 0.01, size=(m, 3))
+    k = m // 4
+    dst[:k] += rng.normal(size=(k, 3)) * 3
+    t, inl = ctx.tls_translation(src, dst, 0.02, 1.0)
+    ot, oinl = orc.tls_translation(src, dst, 0.02, 1.0)
+    assert np.allclose(t, ot, atol=1e-12)
+    assert np.array_equal(inl, oinl)
+
+
+@pytest.mark.parametrize("X,r,ref", [
+    ([0.5, 1, 0.6, 0.7, 1.2], [0.9, 0.9, 0.4, 0.5, 0.4], 0.8383),
+    ([0.5, 1, 0.6, 0.7, 1.2, 10], [0.9, 0.9, 0.4, 0.5, 0.4, 0.5], 0.8383),
+    ([0.5, 1, 0.6, 20, 16, 10], [0.9, 0.9, 0.4, 0.5, 0.4, 0.5], 0.6425)])
+def test_scalar_tls_kat(ctx, X, r, ref):  # tls-test.cc:21-86
+    est, inl = ctx.scalar_tls(X, r)
+    oest, oinl = orc.scalar_tls(X, r)
+    assert abs(est - ref) < 1e-3
+    assert est == oest and np.array_equal(inl, oinl)
+
+
+# ------------------------------------------------------------------ whole path
+SOLVE_CASES = [("C2", 800), ("C2cube", 1200), ("C3", 2500), ("C4", 600), ("C5", 1500)]
+
+
+@pytest.mark.parametrize("cfg,n", SOLVE_CASES)
+def test_solve_vs_oracle(ctx, cfg, n):
+    pr = synth.config_problem(cfg, 2, n=n)
+    kw = fixed_params(pr["noise_bound"])
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    assert g["valid"] and o["valid"]
+    assert np.array_equal(g["clique"], o["clique"])  # identical max-clique inlier index set
+    assert g["proven"]
+    assert g["n_edges"] == o["sol"].n_edges
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL
+    assert np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+    assert g["scale"] == 1.0
+    assert np.array_equal(g["trans_inliers"], o["trans_inliers"])
+    assert np.mean(g["rot_inliers"] != o["rot_inliers"]) <= 0.01
+
+
+def test_solve_bunny_c1(ctx):
+    """BASELINE config C1 (examples/teaser_cpp_ply/teaser_cpp_ply.cc) with a fixed seed."""
+    pr = synth.bunny_problem(os.path.join(synth.GOLDEN_DIR, "bun_zipper_res3.ply"))
+    kw = fixed_params(pr["noise_bound"], rotation_cost_threshold=0.005)
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    assert np.array_equal(g["clique"], o["clique"])
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL
+    assert np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+    assert synth.angular_error(pr["R"], g["R"]) < 0.01 and np.linalg.norm(pr["t"] - g["t"]) < 0.01
+
+
+def test_solve_invalid_when_no_clique(ctx):
+    rng = np.random.default_rng(0)
+    src = rng.uniform(size=(50, 3))
+    dst = rng.uniform(size=(50, 3)) * 100
+    kw = fixed_params(1e-6)
+    g = ctx.solve(src, dst, capi.default_params(**kw))
+    o = orc.solve(src, dst, orc.default_params(**kw))
+    assert g["valid"] == o["valid"]
+    if not o["valid"]:
+        assert len(g["clique"]) <= 1
+
+
+def test_solve_outlier_detection_identity(ctx):  # registration-test.cc:394-467
+    for n_out in range(1, 6):
+        rng = np.random.default_rng(100 + n_out)
+        N = 20
+        src = rng.uniform(-1, 1, size=(N, 3))
+        R = synth.random_rotation(rng)
+        t = rng.uniform(-1, 1, size=3)
+        dst = src @ R.T + t
+        out_idx = np.sort(rng.choice(N, size=n_out, replace=False))
+        dst[out_idx] += rng.uniform(5, 10, size=(n_out, 3))
+        g = ctx.solve(src, dst, capi.default_params(**fixed_params(1e-3, rotation_cost_threshold=0.005)))
+        assert synth.angular_error(R, g["R"]) <= 0.2 and np.linalg.norm(g["t"] - t) <= 0.1
+        assert g["clique"].tolist() == sorted(set(range(N)) - set(out_idx.tolist()))
+
+
+def test_solve_none_mode(ctx):
+    pr = synth.config_problem("C2", 9, n=300)
+    src, dst = pr["src"][pr["inliers"]], pr["dst"][pr["inliers"]]
+    kw = fixed_params(pr["noise_bound"], inlier_selection_mode=3)
+    o = orc.solve(src, dst, orc.default_params(**kw))
+    g = ctx.solve(src, dst, capi.default_params(**kw))
+    assert len(g["clique"]) == len(src)
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+def test_solve_batch_matches_single(ctx):
+    prs = [synth.config_problem("C4", b, n=500) for b in range(12)]
+    p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
+    sols, cliques = ctx.solve_batch([q["src"] for q in prs], [q["dst"] for q in prs], p)
+    for b, q in enumerate(prs):
+        g = ctx.solve(q["src"], q["dst"], p)
+        assert np.array_equal(cliques[b], g["clique"])
+        assert np.array_equal(capi.rotation_from_solution_record(sols[b]), g["R"])
+        assert np.array_equal(sols[b]["translation"], g["t"])
+        assert np.array_equal(cliques[b], q["inliers"])
+
+
+def test_solve_batch_ragged(ctx):
+    prs = [synth.config_problem("C2", b, n=n) for b, n in enumerate([200, 333, 64, 500])]
+    p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
+    sols, cliques = ctx.solve_batch([q["src"] for q in prs], [q["dst"] for q in prs], p)
+    for b, q in enumerate(prs):
+        o = orc.solve(q["src"], q["dst"], orc.default_params(**fixed_params(q["noise_bound"])))
+        assert np.array_equal(cliques[b], o["clique"])
+        assert synth.angular_error(o["R"], capi.rotation_from_solution_record(sols[b])) <= ROT_TOL
+
+
+def test_solve_full_size_c2(ctx):
+    pr = synth.config_problem("C2", 0)
+    kw = fixed_params(pr["noise_bound"])
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    assert np.array_equal(g["clique"], o["clique"]) and np.array_equal(g["clique"], pr["inliers"])
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
