@@ -595,6 +595,7 @@ struct CliqueSearch {
   int n, W;
   std::atomic<int> best;
   std::vector<int> best_clique;  // in compact labels
+  const int* orig = nullptr;     // compact label -> original vertex id (for the canonical tie-break)
   double deadline_ms;
   std::atomic<bool> timed_out;
   std::atomic<i64> nodes;
@@ -609,7 +610,11 @@ struct CliqueSearch {
     uint64_t* P = S.bits[depth].data();
     uint64_t* Q = P + W;
     uint64_t* R = Q + W;
-    int kmin = best.load(std::memory_order_relaxed) - (int)C.size() + 1;
+    // Canonical result: ALL maximum cliques are enumerated (branches are cut only when they cannot even
+    // tie the incumbent) and the lexicographically smallest sorted index set is kept.  When the maximum
+    // clique is unique this is exactly the reference's answer; when it is not, the reference (PMC, multi-
+    // threaded) returns an unspecified one of them.
+    int kmin = best.load(std::memory_order_relaxed) - (int)C.size();
     if (kmin < 1) kmin = 1;
     int pc = 0;
     for (int w = 0; w < W; ++w) pc += __builtin_popcountll(P[w]);
@@ -641,7 +646,7 @@ struct CliqueSearch {
     for (int i = cnt - 1; i >= 0; --i) {
       int v = ord[2 * i];
       int col = ord[2 * i + 1];
-      if ((int)C.size() + col <= best.load(std::memory_order_relaxed)) return;
+      if ((int)C.size() + col < best.load(std::memory_order_relaxed)) return;
       const uint64_t* nv = A->row(v);
       bool any = false;
       for (int w = 0; w < W; ++w) {
@@ -650,12 +655,19 @@ struct CliqueSearch {
       }
       C.push_back(v);
       if (!any) {
-        if ((int)C.size() > best.load(std::memory_order_relaxed)) {
+        if ((int)C.size() >= best.load(std::memory_order_relaxed)) {
 #pragma omp critical(orc_clique_update)
           {
             if ((int)C.size() > best.load()) {
               best_clique = C;
               best.store((int)C.size());
+            } else if ((int)C.size() == best.load()) {
+              std::vector<int> a(C.size()), b(best_clique.size());
+              for (size_t q = 0; q < C.size(); ++q) a[q] = orig[C[q]];
+              for (size_t q = 0; q < best_clique.size(); ++q) b[q] = orig[best_clique[q]];
+              std::sort(a.begin(), a.end());
+              std::sort(b.begin(), b.end());
+              if (b.size() != a.size() || a < b) best_clique = C;
             }
           }
         }
@@ -774,16 +786,19 @@ std::vector<int> find_max_clique(const std::vector<std::vector<int>>& adj, int m
     info->ub = ub;
   }
   if (lb == 0) return C;   // :93-98  (graph without edges: PMC's heuristic reports 0)
-  if (lb == ub) return C;  // :100-102
-  if (mode != MODE_PMC_EXACT) return C;  // :105 (PMC_HEU, or KCORE_HEU below threshold)
+  // graph.cc:100-102 returns the heuristic clique when lb == ub, and :105 skips the exact search unless
+  // PMC_EXACT.  In PMC_EXACT mode this restatement ALWAYS runs the enumeration below so that ties between
+  // maximum cliques are resolved canonically (lexicographically smallest sorted index set); with a unique
+  // maximum clique the result equals the reference's in both branches.
+  if (mode != MODE_PMC_EXACT) return C;  // PMC_HEU, or KCORE_HEU below threshold
 
   // ---- exact search (graph.cc:105-122; pmc::pmcx_maxclique) ----
   if (info) info->exact_ran = 1;
-  // k-core pruning: only vertices with core >= lb can be in a clique of size lb+1
+  // k-core pruning: a vertex of a clique of size >= lb has core number >= lb-1
   std::vector<int> keep;
   for (int i = 0; i < n; ++i) {
     int v = order[i];  // ascending core/degeneracy order
-    if (core[v] >= lb) keep.push_back(v);
+    if (core[v] >= lb - 1) keep.push_back(v);
   }
   const int nk = (int)keep.size();
   if (nk == 0) return C;
@@ -804,6 +819,8 @@ std::vector<int> find_max_clique(const std::vector<std::vector<int>>& adj, int m
   S.n = nk;
   S.W = A.W;
   S.best.store(lb);
+  S.orig = keep.data();
+  for (int v : C) S.best_clique.push_back(label[v]);  // heuristic clique = first incumbent
   S.timed_out.store(false);
   S.nodes.store(0);
   S.deadline_ms = now_ms() + time_limit_s * 1000.0;
@@ -830,13 +847,13 @@ std::vector<int> find_max_clique(const std::vector<std::vector<int>>& adj, int m
         P[w] = m;
         pc += __builtin_popcountll(m);
       }
-      if (pc + 1 <= S.best.load()) continue;
+      if (pc + 1 < S.best.load()) continue;
       Cc.clear();
       Cc.push_back(i);
       S.expand(Cc, scratch, 0);
     }
   }
-  if ((int)S.best_clique.size() > lb) {
+  if ((int)S.best_clique.size() >= lb) {
     C.clear();
     for (int l : S.best_clique) C.push_back(keep[l]);
   }

@@ -25,7 +25,7 @@ struct tzr_ctx {
   uint32_t flags = 0;
   int num_sms = 148;
   // device buffers (grow-only)
-  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, alive_cnt, root_ctr, lock, flg, stack, cv,
+  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, stack, cv,
       centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc;
   // pinned host staging
   void* h_pin = nullptr;
@@ -33,7 +33,7 @@ struct tzr_ctx {
   // last batch geometry
   Batch last{};
   bool have_last = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start | prep | graph tiles | clique (incl. degrees) | rot+trans
 };
 
 namespace {
@@ -119,6 +119,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
   ENS(clq, Bn * sizeof(int32_t));
   ENS(L, (size_t)B * sizeof(int32_t));
   ENS(alive, (size_t)B * W32 * sizeof(uint32_t));
+  ENS(best_bits, (size_t)B * W32 * sizeof(uint32_t));
   ENS(alive_cnt, (size_t)B * sizeof(int32_t));
   ENS(root_ctr, (size_t)B * sizeof(int32_t));
   ENS(lock, (size_t)B * sizeof(int32_t));
@@ -164,6 +165,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
   bt.clq = (int32_t*)ctx->clq.p;
   bt.L = (int32_t*)ctx->L.p;
   bt.alive = (uint32_t*)ctx->alive.p;
+  bt.best_bits = (uint32_t*)ctx->best_bits.p;
   bt.alive_cnt = (int32_t*)ctx->alive_cnt.p;
   bt.root_ctr = (int32_t*)ctx->root_ctr.p;
   bt.lock = (int32_t*)ctx->lock.p;
@@ -243,8 +245,8 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
   int nl = 0;
   if (mode != 3) {
     launch_graph(bt, st);
-    launch_degree(bt, st);
     cudaEventRecord(ctx->ev[2], st);
+    launch_degree(bt, st);
     nl += 2;
     launch_clique(bt, p, mode, st, &nl);
   } else {
@@ -330,7 +332,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
-                    &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->alive_cnt, &ctx->root_ctr,
+                    &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
                     &ctx->misc};
@@ -603,12 +605,29 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
   double* h_dst = (double*)(hp + per * B);
   tzr_solution* h_sol = (tzr_solution*)(hp + 2 * per * B);
   int32_t* h_clq = (int32_t*)(hp + 2 * per * B + (size_t)B * sizeof(tzr_solution));
-  for (int b = 0; b < B; ++b) {
-    memcpy((char*)h_src + per * b, src[b], per);
-    memcpy((char*)h_dst + per * b, dst[b], per);
+  // Fast path: the caller's buffers are one contiguous, page-locked block (e.g. a pinned batch tensor) ->
+  // DMA straight from user memory.  Otherwise stage through the context's pinned buffer.
+  bool contiguous = true;
+  for (int b = 1; b < B; ++b)
+    contiguous &= (src[b] == src[0] + (size_t)b * n * 3) && (dst[b] == dst[0] + (size_t)b * n * 3);
+  bool pinned = false;
+  if (contiguous) {
+    cudaPointerAttributes a1, a2;
+    if (cudaPointerGetAttributes(&a1, src[0]) == cudaSuccess && cudaPointerGetAttributes(&a2, dst[0]) == cudaSuccess)
+      pinned = (a1.type == cudaMemoryTypeHost) && (a2.type == cudaMemoryTypeHost);
+    cudaGetLastError();
   }
-  CK(cudaMemcpyAsync((void*)bt.src, h_src, per * B, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync((void*)bt.dst, h_dst, per * B, cudaMemcpyHostToDevice, st));
+  if (contiguous && pinned) {
+    CK(cudaMemcpyAsync((void*)bt.src, src[0], per * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)bt.dst, dst[0], per * B, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int b = 0; b < B; ++b) {
+      memcpy((char*)h_src + per * b, src[b], per);
+      memcpy((char*)h_dst + per * b, dst[b], per);
+    }
+    CK(cudaMemcpyAsync((void*)bt.src, h_src, per * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync((void*)bt.dst, h_dst, per * B, cudaMemcpyHostToDevice, st));
+  }
   rc = run_pipeline(ctx, bt, *params);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));

@@ -11,15 +11,19 @@
 //        vertices (adjacent to every other candidate) join the clique at once; otherwise the vertex
 //        of largest in-P degree joins and P &= N(u) }.
 //   K2 clique_peel   (1 CTA / problem)  picks the best heuristic clique (size L), then peels the
-//        graph to its L-core (a clique of size L+1 needs L neighbours): if nothing survives, L is
-//        proven optimal — the common case for TEASER-style inlier graphs (this is what the
-//        reference's `lb == ub` early-out, graph.cc:100-102, achieves through PMC's k-core bound).
+//        graph to its (L-1)-core (a member of a clique of size >= L has L-1 neighbours).  For
+//        TEASER-style inlier graphs only the clique itself survives — the situation in which the
+//        reference's `lb == ub` early-out (graph.cc:100-102) fires through PMC's k-core bound.
 //   K3 clique_exact  (G CTAs / problem, one warp per root vertex)  branch and bound over the
 //        survivors: root v owns the cliques whose smallest index is v (P = N(v) ∩ alive ∩ {u>v});
-//        every node is reduced by in-P degree rules (universal vertices, vertices that cannot reach
-//        L+1), bounded by greedy sequential colouring (branch only on vertices whose colour exceeds
-//        L - |C|), and expanded depth-first with an explicit stack in global memory.  The incumbent
-//        is shared through L[b] (atomic) + a spin lock for the vertex list.
+//        every node is reduced by in-P degree rules (universal vertices join at once, vertices that
+//        cannot reach size L leave), bounded by greedy sequential colouring (branch only on vertices
+//        whose colour reaches L - |C|), and expanded depth-first with an explicit stack in global
+//        memory.  Branches are cut only when they cannot even TIE the incumbent, so every maximum
+//        clique is enumerated and the lexicographically smallest index set is returned: the answer
+//        is deterministic and independent of warp scheduling (when the maximum clique is unique —
+//        the normal case — it is the reference's answer; PMC returns an unspecified one on ties).
+//        The incumbent is shared through L[b] (atomic) + a spin lock for the vertex list/bitset.
 //
 // Bit-parallel integer work, L2-resident bitset: no tensor cores, no meaningful HBM roofline.
 #include "tzr_internal.cuh"
@@ -254,6 +258,17 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
     bt.lock[b] = 0;
     bt.flags[b] = 0;
   }
+  // incumbent as a bitset (canonical tie-break in the exact phase compares bitsets)
+  {
+    uint32_t* bb = bt.best_bits + (size_t)b * W;
+    for (int x = tid; x < W; x += blockDim.x) A[x] = 0u;
+    __syncthreads();
+    const int32_t* srcq = bt.hclq + ((size_t)b * kHeurRoots + win) * n;
+    for (int i = tid; i < L; i += blockDim.x) atomicOr(&A[srcq[i] >> 5], 1u << (srcq[i] & 31));
+    __syncthreads();
+    for (int x = tid; x < W; x += blockDim.x) bb[x] = A[x];
+    __syncthreads();
+  }
   uint32_t* alive_g = bt.alive + (size_t)b * W;
   if (mode != 0 || L == 0) {
     for (int x = tid; x < W; x += blockDim.x) alive_g[x] = 0u;
@@ -265,7 +280,7 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
     uint32_t m = 0;
     for (int k = 0; k < 32; ++k) {
       const int v = x * 32 + k;
-      if (v < n && deg[v] >= L) m |= 1u << k;
+      if (v < n && deg[v] >= L - 1) m |= 1u << k;
     }
     A[x] = m;
     An[x] = m;
@@ -284,7 +299,7 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
         int d = 0;
         for (int y = lane; y < W; y += 32) d += __popc(rv[y] & A[y]);
         d = __reduce_add_sync(0xffffffffu, d);
-        if (d < L && lane == 0) {
+        if (d < L - 1 && lane == 0) {
           atomicAnd(&An[x], ~(1u << bit));
           s_changed = 1;
         }
@@ -350,15 +365,15 @@ struct WarpCtx {
   volatile int32_t* Lp;
 };
 
-// Reduce the node in Pc.  Returns: 0 pruned, 1 leaf (Pc empty, csz is a new record), 2 continue.
+// Reduce the node in Pc.  Returns: 0 pruned, 1 leaf (Pc empty, csz >= incumbent size), 2 continue.
 __device__ int node_reduce(WarpCtx& c, int& csz) {
   const int W = c.W, lane = c.lane;
   for (int round = 0; round < 8; ++round) {
     const int cnt = warp_popc(c.Pc, W, lane);
     const int Lc = *c.Lp;
-    if (csz + cnt <= Lc) return 0;
+    if (csz + cnt < Lc) return 0;  // cannot even tie the incumbent (ties are enumerated: canonical result)
     if (cnt == 0) return 1;
-    const int need = Lc - csz;  // a candidate must have >= need neighbours inside P
+    const int need = Lc - csz - 1;  // a candidate must have >= need neighbours inside P to reach size Lc
     for (int x = lane; x < W; x += 32) c.Q[x] = c.Pc[x];
     __syncwarp();
     bool changed = false;
@@ -392,13 +407,13 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     if (!changed) {
       const int cnt2 = cnt - added;
       const int Lc2 = *c.Lp;
-      if (csz + cnt2 <= Lc2) return 0;
+      if (csz + cnt2 < Lc2) return 0;
       if (cnt2 == 0) return 1;
       return 2;
     }
   }
   const int cnt = warp_popc(c.Pc, W, lane);
-  if (csz + cnt <= *c.Lp) return 0;
+  if (csz + cnt < *c.Lp) return 0;
   if (cnt == 0) return 1;
   return 2;
 }
@@ -406,7 +421,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
 // Greedy sequential colouring of Pc; Bs = vertices whose colour >= kmin.  Returns |Bs|.
 __device__ int node_colour(WarpCtx& c, int csz) {
   const int W = c.W, lane = c.lane;
-  int kmin = *c.Lp - csz + 1;
+  int kmin = *c.Lp - csz;  // colour k bounds cliques by k: need csz + k >= L to tie or beat
   if (kmin < 1) kmin = 1;
   for (int x = lane; x < W; x += 32) {
     c.Q[x] = c.Pc[x];
@@ -444,18 +459,53 @@ __device__ int node_colour(WarpCtx& c, int csz) {
   return nB;
 }
 
+// Offer the clique cv[0..csz) as incumbent.  Larger wins; on equal size the lexicographically smaller
+// sorted index set wins (== the set that owns the lowest vertex of the symmetric difference), which makes
+// the final answer independent of the order in which warps find cliques.
 __device__ void record_clique(WarpCtx& c, int csz) {
-  if (c.lane == 0) {
-    int32_t* lock = c.bt->lock + c.b;
+  const int W = c.W, lane = c.lane;
+  for (int x = lane; x < W; x += 32) c.Q[x] = 0u;
+  __syncwarp();
+  for (int i = lane; i < csz; i += 32) {
+    const int v = c.cv[i];
+    atomicOr(&c.Q[v >> 5], 1u << (v & 31));
+  }
+  __syncwarp();
+  int32_t* lock = c.bt->lock + c.b;
+  if (lane == 0) {
     while (atomicCAS(lock, 0, 1) != 0) {
     }
     __threadfence();
-    if (csz > *c.Lp) {
-      int32_t* dst = c.bt->clq + (size_t)c.b * c.n;
-      for (int i = 0; i < csz; ++i) dst[i] = c.cv[i];
-      __threadfence();
-      atomicExch(c.bt->L + c.b, csz);
+  }
+  __syncwarp();
+  const int Lc = *c.Lp;
+  volatile uint32_t* bb = c.bt->best_bits + (size_t)c.b * W;
+  bool take = csz > Lc;
+  if (csz == Lc) {
+    for (int base = 0; base < W; base += 32) {
+      const int x = base + lane;
+      const uint32_t mine = x < W ? c.Q[x] : 0u;
+      const uint32_t diff = x < W ? (mine ^ bb[x]) : 0u;
+      const unsigned nz = __ballot_sync(0xffffffffu, diff != 0u);
+      if (nz) {
+        const int srcl = __ffs(nz) - 1;
+        const uint32_t d0 = __shfl_sync(0xffffffffu, diff, srcl);
+        const uint32_t m0 = __shfl_sync(0xffffffffu, mine, srcl);
+        take = ((m0 >> (__ffs(d0) - 1)) & 1u) != 0u;
+        break;
+      }
     }
+  }
+  if (take) {
+    int32_t* dst = c.bt->clq + (size_t)c.b * c.n;
+    for (int i = lane; i < csz; i += 32) dst[i] = c.cv[i];
+    for (int x = lane; x < W; x += 32) bb[x] = c.Q[x];
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(c.bt->L + c.b, csz);
+  }
+  __syncwarp();
+  if (lane == 0) {
     __threadfence();
     atomicExch(lock, 0);
   }
@@ -521,9 +571,8 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
           break;
         }
         const int r = node_reduce(c, csz);
-        bool descend = false; (void)descend;
         if (r == 1) {
-          if (csz > *c.Lp) record_clique(c, csz);
+          if (csz >= *c.Lp) record_clique(c, csz);
         } else if (r == 2) {
           const int nB = node_colour(c, csz);
           if (nB > 0) {
@@ -538,11 +587,9 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
               if (lane == 0) c.centry[depth] = csz;
               __syncwarp();
               ++depth;
-              descend = true;
             }
           }
         }
-        (void)descend;
         fresh = false;
       }
       // ---- branch: next candidate of the top saved level
@@ -552,10 +599,10 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
       uint32_t* Bd = Pd + W;
       const int ce = c.centry[d];
       int xf;
-      // cheap level bound: every remaining clique of this level has size <= ce + |P_d|
+      // cheap level bound: every remaining clique of this level has size <= ce + |P_d| (ties still explored)
       const int cntP = warp_popc(Pd, W, lane);
       int u = -1;
-      if (ce + cntP > *c.Lp) u = warp_first_bit(Bd, W, lane, 0, &xf);
+      if (ce + cntP >= *c.Lp) u = warp_first_bit(Bd, W, lane, 0, &xf);
       if (u < 0) {
         --depth;
         continue;

@@ -51,7 +51,8 @@ struct Batch {
   int32_t* hsize;         // B*kHeurRoots
   int32_t* clq;           // B*n incumbent clique (unsorted)
   int32_t* L;             // B incumbent size
-  uint32_t* alive;        // B*pitch32(n) bitset of vertices surviving the L-core peel
+  uint32_t* alive;        // B*pitch32(n) bitset of vertices surviving the (L-1)-core peel
+  uint32_t* best_bits;    // B*pitch32(n) incumbent clique as a bitset (canonical tie-break)
   int32_t* alive_cnt;     // B
   int32_t* root_ctr;      // B work counter for the exact phase
   int32_t* lock;          // B spin lock for incumbent updates

@@ -157,6 +157,7 @@ def test_clique_random_graphs(ctx, seed):
     assert len(gc) == len(oc)
     assert all(A[a, b] for a in gc for b in gc if a != b)
     assert np.all(np.diff(gc) > 0)
+    assert np.array_equal(gc, oc)  # canonical (lexicographically smallest) maximum clique, ties included
 
 
 def test_clique_toy_graphs(ctx):
@@ -174,6 +175,22 @@ def test_clique_toy_graphs(ctx):
     assert len(gc) == 0  # PMC reports lb = 0 on an edgeless graph; solve() then returns valid = false
 
 
+def test_clique_canonical_tie_break(ctx):
+    import itertools
+    A = np.zeros((8, 8), dtype=bool)
+    for K in ([0, 1, 2, 3], [4, 5, 6, 7]):
+        for a, b in itertools.combinations(K, 2):
+            A[a, b] = A[b, a] = True
+    gc, proven = ctx.max_clique(_bits_from_dense(A), 8)
+    assert gc.tolist() == [0, 1, 2, 3] and proven
+    A = np.zeros((6, 6), dtype=bool)
+    for K in ([2, 3, 4, 5], [0, 3, 4, 5]):
+        for a, b in itertools.combinations(K, 2):
+            A[a, b] = A[b, a] = True
+    gc, proven = ctx.max_clique(_bits_from_dense(A), 6)
+    assert gc.tolist() == [0, 3, 4, 5]
+
+
 @pytest.mark.parametrize("cfg,n", [("C2", 1000), ("C2cube", 1500), ("C3", 3000), ("C5", 2000)])
 def test_clique_on_inlier_graphs(ctx, cfg, n):
     pr = synth.config_problem(cfg, 1, n=n)
@@ -181,7 +198,7 @@ def test_clique_on_inlier_graphs(ctx, cfg, n):
     oc, info = orc.max_clique_bits(bits, n)
     gc, proven = ctx.max_clique(bits, n, mode=0)
     assert proven
-    assert np.array_equal(gc, oc)  # unique maximum clique -> identical index set
+    assert np.array_equal(gc, oc)  # identical index set (canonical tie-break on both sides)
 
 
 # ------------------------------------------------------------------ stage 3: GNC-TLS rotation

@@ -95,3 +95,22 @@ def test_synthetic_configs_small(cfg, n):
     assert set(pr["inliers"].tolist()) <= set(out["clique"].tolist())
     assert synth.angular_error(pr["R"], out["R"]) < 0.05
     assert np.linalg.norm(out["t"] - pr["t"]) < 0.05
+
+
+def test_canonical_tie_break():
+    """Several maximum cliques: the oracle (and the GPU path) return the lexicographically smallest sorted
+    index set; the reference (PMC, multi-threaded) returns an unspecified one of them."""
+    # two disjoint K4
+    adj = [[j for j in range(4) if j != i] for i in range(4)] + [[4 + j for j in range(4) if j != i] for i in range(4)]
+    c, _ = orc.max_clique_adj(adj, threads=3)
+    assert sorted(c.tolist()) == [0, 1, 2, 3]
+    # overlapping K4s {2,3,4,5} and {0,3,4,5}
+    import itertools
+    n = 6
+    A = np.zeros((n, n), dtype=bool)
+    for K in ([2, 3, 4, 5], [0, 3, 4, 5]):
+        for a, b in itertools.combinations(K, 2):
+            A[a, b] = A[b, a] = True
+    adj = [np.nonzero(A[i])[0].tolist() for i in range(n)]
+    c, _ = orc.max_clique_adj(adj, threads=2)
+    assert sorted(c.tolist()) == [0, 3, 4, 5]
