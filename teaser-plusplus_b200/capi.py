@@ -204,9 +204,9 @@ class Context:
         self._ck(lib().tzr_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
     def last_stage_ms(self):
-        v = (C.c_double * 4)()
-        self._ck(lib().tzr_last_stage_ms(self._h, C.byref(v, 0), C.byref(v, 8), C.byref(v, 16), C.byref(v, 24)))
-        return dict(prep=v[0], graph=v[1], clique=v[2], rot_trans=v[3])
+        v = [C.c_double() for _ in range(4)]
+        self._ck(lib().tzr_last_stage_ms(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3])))
+        return dict(prep=v[0].value, graph=v[1].value, clique=v[2].value, rot_trans=v[3].value)
 
     # -- stages
     def graph_build(self, src, dst, beta):

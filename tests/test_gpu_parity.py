@@ -222,9 +222,11 @@ def test_gnc_tls_iterating(ctx, seed):
     g = ctx.gnc_tls_rotation(src, dst, 0.05, 1.4, 100, 1e-12)
     assert o["iterations"] > 3
     assert abs(g["iterations"] - o["iterations"]) <= 1
-    assert synth.angular_error(o["R"], g["R"]) < 1e-9
+    # summation order differs (block tree vs sequential) and the 1e-12 stop rule may fire one iteration
+    # apart: compare within a small fraction of the 1e-4 rad budget
+    assert synth.angular_error(o["R"], g["R"]) < 1e-6
     assert np.mean(g["inliers"] != o["inliers"]) < 0.01
-    assert abs(g["cost"] - o["cost"]) <= 1e-9 * max(1.0, abs(o["cost"]))
+    assert abs(g["cost"] - o["cost"]) <= 1e-6 * max(1.0, abs(o["cost"]))
     assert synth.angular_error(R, g["R"]) < 0.05
 
 
