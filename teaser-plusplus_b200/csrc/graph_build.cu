@@ -35,8 +35,10 @@ __device__ __forceinline__ double tim_norm_exact(const double* __restrict__ p, i
   return __dsqrt_rn(s);
 }
 
-__device__ __forceinline__ bool edge_exact(const double* __restrict__ src, const double* __restrict__ dst, int i,
-                                           int j, double beta) {
+// Deliberately NOT inlined: the exact path runs for ~1e-4 of the pairs; keeping its two DSQRT expansions out
+// of the unrolled sweep keeps the hot loop small enough for the instruction cache.
+__device__ __noinline__ bool edge_exact(const double* __restrict__ src, const double* __restrict__ dst, int i,
+                                        int j, double beta) {
   const double d1 = tim_norm_exact(src, i, j);
   const double d2 = tim_norm_exact(dst, i, j);
   return fabs(__dsub_rn(d1, d2)) <= beta;  // (v1_dist - v2_dist).abs() <= beta   registration.cc:442
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     }
     gc.c2 = (float)(2.0 * gam2 * gam2 * up);
     gc.g2 = (float)(gam2 * gam2 * gam2 * gam2 * dn);
-    gc.smin = (float)(16.0 * gam2 * gam2 * up);
+    gc.smin = use64 ? __int_as_float(0x7f800000) : (float)(16.0 * gam2 * gam2 * up);  // +inf: every pair exact
     gc.use_fp64 = use64;
     bt.gc[b] = gc;
     bt.n_edges2[b] = 0ull;
@@ -155,14 +157,16 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// graph tile kernel: one CTA per 128x128 tile of the upper triangle (I <= J) of one problem.
-// 8 warps; warp w owns rows [32*(w/2), +32) x cols [64*(w%2), +64) of the tile: lane l keeps the two
-// column points (l, l+32) in registers and sweeps the 32 row points broadcast from shared memory.
+// graph tile kernel: one CTA (4 warps) per 128x128 tile of the upper triangle (I <= J) of one problem.
+// Warp w owns rows [32w, 32w+32) x all 128 columns of the tile: lane l keeps the four column points
+// (l, l+32, l+64, l+96) in registers and sweeps the 32 row points broadcast from shared memory, i.e. four
+// pair predicates per lane per step (amortises the shared-memory loads and the loop overhead).
 // Row words come from __ballot_sync; the transposed (column) words are accumulated per lane, so the
-// symmetric half of the bitset costs no extra predicate evaluations.
+// symmetric half of the bitset costs no extra predicate evaluations.  Validity (i,j < n, i != j) is applied
+// as word masks after the sweep, not per pair.
 // ------------------------------------------------------------------------------------------------
 struct PairEval {
-  bool sure, amb;
+  bool sure, decided;
 };
 
 __device__ __forceinline__ PairEval classify(const float4 is, const float4 id, const float4 js, const float4 jd,
@@ -177,14 +181,16 @@ __device__ __forceinline__ PairEval classify(const float4 is, const float4 id, c
   const float r1 = fmaf(c1, s, -g1);
   const float r2 = fmaf(c2, s, -g2);
   PairEval e;
-  const bool big = s >= smin;
-  e.sure = big && (tt <= r1);
-  const bool non = big && (tt > r2);
-  e.amb = !(e.sure || non);
+  const bool small = s < smin;          // tiny TIMs (and everything, when smin = +inf): always re-checked
+  e.sure = !small && (tt <= r1);        // surely an edge
+  e.decided = e.sure || (!small && (tt > r2));  // ... or surely not an edge
   return e;
 }
 
-__global__ void __launch_bounds__(kGraphThreads, 3) graph_tile_kernel(Batch bt) {
+constexpr int kGraphWarps = kGraphThreads / 32;  // 4
+
+template <bool kVerify>
+__global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) {
   const int b = blockIdx.y;
   const int n = bt.n;
   const int nt = (n + kTile - 1) / kTile;
@@ -203,9 +209,7 @@ __global__ void __launch_bounds__(kGraphThreads, 3) graph_tile_kernel(Batch bt) 
 
   const GraphConsts* gcp = bt.gc + b;
   const float c1 = gcp->c1, g1 = gcp->g1, c2 = gcp->c2, g2 = gcp->g2, smin = gcp->smin;
-  const bool force64 = gcp->use_fp64 != 0;
   const double beta = gcp->beta;
-  const bool verify = (bt.flags_dbg & 2u) != 0;
 
   const float4* sf = bt.sf + (size_t)b * n;
   const float4* df = bt.df + (size_t)b * n;
@@ -213,78 +217,118 @@ __global__ void __launch_bounds__(kGraphThreads, 3) graph_tile_kernel(Batch bt) 
   const double* dst = bt.dst + (size_t)b * n * 3;
 
   const int tid = threadIdx.x;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   {
-    const int t = tid & (kTile - 1);
-    const int i = I * kTile + t;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < kTile)
-      s_is[t] = (i < n) ? sf[i] : z;
-    else
-      s_id[t] = (i < n) ? df[i] : z;
+    const int i = I * kTile + tid;
+    s_is[tid] = (i < n) ? sf[i] : z4;
+    s_id[tid] = (i < n) ? df[i] : z4;
   }
   const int w = tid >> 5, lane = tid & 31;
-  const int ri = w >> 1, ch = w & 1;
-  const int j0 = J * kTile + 64 * ch + lane, j1 = j0 + 32;
-  const bool vj0 = j0 < n, vj1 = j1 < n;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 j0s = vj0 ? sf[j0] : z4, j0d = vj0 ? df[j0] : z4;
-  const float4 j1s = vj1 ? sf[j1] : z4, j1d = vj1 ? df[j1] : z4;
+  const int jb = J * kTile + lane;
+  float4 js[4], jd[4];
+  bool vj[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int j = jb + 32 * c;
+    vj[c] = j < n;
+    js[c] = vj[c] ? sf[j] : z4;
+    jd[c] = vj[c] ? df[j] : z4;
+  }
   __syncthreads();
 
-  uint32_t rowA = 0, rowB = 0, colA = 0, colB = 0;
-  const int ibase = I * kTile + 32 * ri;
+  uint32_t roww[4] = {0u, 0u, 0u, 0u}, colw[4] = {0u, 0u, 0u, 0u};
+  const int ibase = I * kTile + 32 * w;
+  const int nrows = min(32, n - ibase);  // may be <= 0 for the last row block
+  // ---- hot sweep.  Kept SMALL on purpose (unroll 2, ~3.5 KB of SASS): a fully unrolled sweep with the exact
+  // path inlined was instruction-fetch bound (ncu: stall_no_instructions dominant).  Steps that contain an
+  // undecided pair are only recorded here (warp-uniform bit mask) and revisited after the sweep.
+  uint32_t ambmask = 0u;
+  uint32_t bit = 1u;
+#pragma unroll 2
+  for (int ii = 0; ii < nrows; ++ii, bit <<= 1) {
+    const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
+    bool all_decided = true;
 #pragma unroll
-  for (int ii = 0; ii < 32; ++ii) {
-    const int i = ibase + ii;
-    if (i >= n) break;  // warp-uniform
-    const float4 is = s_is[32 * ri + ii], id = s_id[32 * ri + ii];
-    PairEval e0 = classify(is, id, j0s, j0d, c1, g1, c2, g2, smin);
-    PairEval e1 = classify(is, id, j1s, j1d, c1, g1, c2, g2, smin);
-    const bool ok0 = vj0 && (i != j0), ok1 = vj1 && (i != j1);
-    bool p0 = ok0 && e0.sure, p1 = ok1 && e1.sure;
-    bool a0 = ok0 && (e0.amb || force64), a1 = ok1 && (e1.amb || force64);
-    if (__any_sync(0xffffffffu, a0 || a1)) {
-      if (a0) p0 = edge_exact(src, dst, i, j0, beta);
-      if (a1) p1 = edge_exact(src, dst, i, j1, beta);
-      if (bt.rechecks) {
-        const unsigned m0 = __ballot_sync(0xffffffffu, a0), m1 = __ballot_sync(0xffffffffu, a1);
-        if (lane == 0) atomicAdd(bt.rechecks, (unsigned long long)(__popc(m0) + __popc(m1)));
-      }
+    for (int c = 0; c < 4; ++c) {
+      const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+      all_decided = all_decided && e.decided;
+      const uint32_t m = __ballot_sync(0xffffffffu, e.sure);
+      if (lane == ii) roww[c] = m;
+      colw[c] |= e.sure ? bit : 0u;
     }
-    if (verify) {
+    if (!__all_sync(0xffffffffu, all_decided)) ambmask |= bit;
+  }
+  // ---- rare: steps with pairs inside the ambiguous band -> exact FP64 sequence for those lanes
+  while (ambmask) {
+    const int ii = __ffs(ambmask) - 1;
+    ambmask &= ambmask - 1;
+    const int i = ibase + ii;
+    const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
+    int nre = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = jb + 32 * c;
+      const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+      bool ex = false;
+      if (!e.decided && vj[c] && j != i) {
+        ex = edge_exact(src, dst, i, j, beta);
+        ++nre;
+      }
+      const uint32_t mex = __ballot_sync(0xffffffffu, ex);
+      if (lane == ii) roww[c] |= mex;
+      colw[c] |= ex ? (1u << ii) : 0u;
+    }
+    if (bt.rechecks) {
+      nre = __reduce_add_sync(0xffffffffu, nre);
+      if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
+    }
+  }
+  if (kVerify) {
+    // debug: every DECIDED pair is re-evaluated exactly; disagreements are counted (must stay 0)
+    for (int ii = 0; ii < nrows; ++ii) {
+      const int i = ibase + ii;
+      const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
       int bad = 0;
-      if (ok0 && !a0) bad += (edge_exact(src, dst, i, j0, beta) != p0);
-      if (ok1 && !a1) bad += (edge_exact(src, dst, i, j1, beta) != p1);
+      for (int c = 0; c < 4; ++c) {
+        const int j = jb + 32 * c;
+        const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+        if (e.decided && vj[c] && j != i) bad += (edge_exact(src, dst, i, j, beta) != e.sure);
+      }
       if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
     }
-    const uint32_t m0 = __ballot_sync(0xffffffffu, p0);
-    const uint32_t m1 = __ballot_sync(0xffffffffu, p1);
-    if (lane == ii) {
-      rowA = m0;
-      rowB = m1;
-    }
-    colA |= p0 ? (1u << ii) : 0u;
-    colB |= p1 ? (1u << ii) : 0u;
   }
-  s_row[32 * ri + lane][2 * ch + 0] = rowA;
-  s_row[32 * ri + lane][2 * ch + 1] = rowB;
-  s_col[64 * ch + lane][ri] = colA;
-  s_col[64 * ch + 32 + lane][ri] = colB;
+  // ---- validity masks: columns >= n, rows >= n, and the diagonal (i == j) of diagonal tiles
+  const uint32_t rmask = nrows >= 32 ? 0xffffffffu : (nrows <= 0 ? 0u : ((1u << nrows) - 1u));
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t cm = __ballot_sync(0xffffffffu, vj[c]);
+    roww[c] &= cm;
+    colw[c] = vj[c] ? (colw[c] & rmask) : 0u;
+    if (I == J) {
+      // row r = 32w + lane holds columns 32c + [0,32): self bit at column r
+      if (c == w) roww[c] &= ~(1u << lane);
+      // column 32c + lane holds rows 32w + [0,32): self bit at row 32c + lane
+      if (c == w) colw[c] &= ~(1u << lane);
+    }
+  }
+  *reinterpret_cast<uint4*>(&s_row[32 * w + lane][0]) = make_uint4(roww[0], roww[1], roww[2], roww[3]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s_col[32 * c + lane][w] = colw[c];
   __syncthreads();
 
   uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * pitch32(n);
   const int P32 = pitch32(n);
-  if (tid < kTile) {
+  {
     const int row = I * kTile + tid;
     if (row < n) {
       const uint4 v = *reinterpret_cast<const uint4*>(&s_row[tid][0]);
       *reinterpret_cast<uint4*>(adj32 + (size_t)row * P32 + 4 * J) = v;
     }
-  } else if (I != J) {
-    const int t = tid - kTile;
-    const int row = J * kTile + t;
+  }
+  if (I != J) {
+    const int row = J * kTile + tid;
     if (row < n) {
-      const uint4 v = *reinterpret_cast<const uint4*>(&s_col[t][0]);
+      const uint4 v = *reinterpret_cast<const uint4*>(&s_col[tid][0]);
       *reinterpret_cast<uint4*>(adj32 + (size_t)row * P32 + 4 * I) = v;
     }
   }
@@ -321,7 +365,10 @@ void launch_prep(const Batch& bt, cudaStream_t st) { prep_kernel<<<bt.B, 256, 0,
 void launch_graph(const Batch& bt, cudaStream_t st) {
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)bt.B);
-  graph_tile_kernel<<<grid, kGraphThreads, 0, st>>>(bt);
+  if (bt.flags_dbg & 2u)
+    graph_tile_kernel<true><<<grid, kGraphThreads, 0, st>>>(bt);
+  else
+    graph_tile_kernel<false><<<grid, kGraphThreads, 0, st>>>(bt);
 }
 
 void launch_degree(const Batch& bt, cudaStream_t st) {

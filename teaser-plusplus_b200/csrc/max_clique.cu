@@ -41,6 +41,30 @@ __device__ __forceinline__ const uint32_t* adj_row32(const Batch& bt, int b, int
   return reinterpret_cast<const uint32_t*>(bt.adj) + ((size_t)b * bt.n + v) * pitch32(bt.n);
 }
 
+// |N(u_k) ∩ S| for up to four vertices at once (k < cnt; unused slots alias u[0]): the row loads of the four
+// vertices are independent, so one warp keeps 4x the memory-level parallelism of a one-vertex-at-a-time loop
+// (these kernels are latency-bound on the L2/HBM-resident bitset, not bandwidth-bound).
+__device__ __forceinline__ void inset_degree4(const Batch& bt, int b, const int u[4], int cnt, const uint32_t* S,
+                                              int W, int lane, int d[4]) {
+  const uint32_t* r0 = adj_row32(bt, b, u[0]);
+  const uint32_t* r1 = adj_row32(bt, b, cnt > 1 ? u[1] : u[0]);
+  const uint32_t* r2 = adj_row32(bt, b, cnt > 2 ? u[2] : u[0]);
+  const uint32_t* r3 = adj_row32(bt, b, cnt > 3 ? u[3] : u[0]);
+  int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+  for (int y = lane; y < W; y += 32) {
+    const uint32_t sw = S[y];
+    const uint32_t a0 = r0[y], a1 = r1[y], a2 = r2[y], a3 = r3[y];
+    d0 += __popc(a0 & sw);
+    d1 += __popc(a1 & sw);
+    d2 += __popc(a2 & sw);
+    d3 += __popc(a3 & sw);
+  }
+  d[0] = __reduce_add_sync(0xffffffffu, d0);
+  d[1] = __reduce_add_sync(0xffffffffu, d1);
+  d[2] = __reduce_add_sync(0xffffffffu, d2);
+  d[3] = __reduce_add_sync(0xffffffffu, d3);
+}
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -182,14 +206,13 @@ __global__ void __launch_bounds__(kHeurThreads) clique_heur_kernel(Batch bt) {
     __syncthreads();
     const int cnt = total;
     if (cnt == 0) break;
-    // ---- in-P degrees: one warp per member
-    for (int k = wid; k < cnt; k += nw) {
-      const int u = list[k];
-      const uint32_t* ru = adj_row32(bt, b, u);
-      int d = 0;
-      for (int x = lane; x < W; x += 32) d += __popc(ru[x] & P[x]);
-      d = __reduce_add_sync(0xffffffffu, d);
-      if (lane == 0) dl[k] = (uint16_t)d;
+    // ---- in-P degrees: one warp per four members
+    for (int k0 = wid * 4; k0 < cnt; k0 += nw * 4) {
+      const int kc = min(4, cnt - k0);
+      int u[4], d[4];
+      for (int q = 0; q < 4; ++q) u[q] = list[k0 + (q < kc ? q : 0)];
+      inset_degree4(bt, b, u, kc, P, W, lane, d);
+      if (lane < kc) dl[k0 + lane] = (uint16_t)(lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]);
     }
     if (tid == 0) s_nuni = 0;
     __syncthreads();
@@ -292,16 +315,23 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
     for (int x = wid; x < W; x += nw) {
       uint32_t m = A[x];  // warp-uniform
       while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const int v = x * 32 + bit;
-        const uint32_t* rv = adj_row32(bt, b, v);
-        int d = 0;
-        for (int y = lane; y < W; y += 32) d += __popc(rv[y] & A[y]);
-        d = __reduce_add_sync(0xffffffffu, d);
-        if (d < L - 1 && lane == 0) {
-          atomicAnd(&An[x], ~(1u << bit));
-          s_changed = 1;
+        int u[4], bits[4], d[4], kc = 0;
+        while (m && kc < 4) {
+          bits[kc] = __ffs(m) - 1;
+          m &= m - 1;
+          u[kc] = x * 32 + bits[kc];
+          ++kc;
+        }
+        for (int q = kc; q < 4; ++q) u[q] = u[0];
+        inset_degree4(bt, b, u, kc, A, W, lane, d);
+        if (lane == 0) {
+          uint32_t clr = 0u;
+          for (int q = 0; q < kc; ++q)
+            if (d[q] < L - 1) clr |= 1u << bits[q];
+          if (clr) {
+            atomicAnd(&An[x], ~clr);
+            s_changed = 1;
+          }
         }
       }
     }
@@ -378,26 +408,34 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     __syncwarp();
     bool changed = false;
     int added = 0;
-    for (int x = 0; x < W; ++x) {
-      uint32_t m = c.Pc[x];  // warp-uniform (shared memory broadcast)
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const int u = x * 32 + bit;
-        const uint32_t* ru = adj_row32(*c.bt, c.b, u);
-        int d = 0;
-        for (int y = lane; y < W; y += 32) d += __popc(ru[y] & c.Pc[y]);
-        d = __reduce_add_sync(0xffffffffu, d);
-        if (d == cnt - 1) {  // universal: belongs to every maximal clique of this node
-          if (lane == 0) {
-            c.Q[x] &= ~(1u << bit);
-            c.cv[csz + added] = u;
-          }
-          ++added;
-        } else if (d < need) {
-          if (lane == 0) c.Q[x] &= ~(1u << bit);
-          changed = true;
+    {
+      int x = 0;
+      uint32_t m = c.Pc[0];  // warp-uniform (shared memory broadcast)
+      while (true) {
+        int u[4], d[4], kc = 0;
+        while (kc < 4) {
+          while (!m && ++x < W) m = c.Pc[x];
+          if (!m) break;
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          u[kc++] = x * 32 + bit;
         }
+        if (kc == 0) break;
+        for (int q = kc; q < 4; ++q) u[q] = u[0];
+        inset_degree4(*c.bt, c.b, u, kc, c.Pc, W, lane, d);
+        for (int q = 0; q < kc; ++q) {
+          if (d[q] == cnt - 1) {  // universal: belongs to every maximal clique of this node
+            if (lane == 0) {
+              c.Q[u[q] >> 5] &= ~(1u << (u[q] & 31));
+              c.cv[csz + added] = u[q];
+            }
+            ++added;
+          } else if (d[q] < need) {
+            if (lane == 0) c.Q[u[q] >> 5] &= ~(1u << (u[q] & 31));
+            changed = true;
+          }
+        }
+        if (kc < 4) break;
       }
     }
     __syncwarp();

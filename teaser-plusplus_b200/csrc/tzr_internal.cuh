@@ -19,7 +19,7 @@ __host__ __device__ inline int pitch32(int n) { return 2 * pitch64(n); }
 __host__ __device__ inline int words64(int n) { return (n + 63) / 64; }
 
 constexpr int kTile = 128;          // graph tile edge (pairs per tile = 128*128)
-constexpr int kGraphThreads = 256;  // 8 warps, each owns a 32x64 sub-tile
+constexpr int kGraphThreads = 128;  // 4 warps, each owns a 32x128 sub-tile (4 pairs per lane per step)
 constexpr int kHeurRoots = 8;       // heuristic start vertices per problem (top degrees)
 constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memory clique kernels
 
