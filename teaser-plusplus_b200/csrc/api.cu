@@ -26,7 +26,7 @@ struct tzr_ctx {
   int num_sms = 148;
   // device buffers (grow-only)
   DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, stack, cv,
-      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc;
+      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx;
   // pinned host staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -213,10 +213,6 @@ __global__ void init_solutions_kernel(tzr_solution* sol, int B) {
 // The fused device pipeline for one uniform batch.  src/dst must already be set in bt.
 int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
   cudaStream_t st = ctx->stream;
-  if (p.estimate_scaling) {
-    ctx->last_error = "estimate_scaling=true (TLSScaleSolver) is not implemented on the GPU path yet";
-    return TZR_ERR_UNSUPPORTED;
-  }
   if (p.rotation_estimation_algorithm != 0) {
     ctx->last_error = "only GNC_TLS rotation is implemented on the GPU path";
     return TZR_ERR_UNSUPPORTED;
@@ -236,12 +232,40 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
     // approximation: the host cannot read globaltimer, so the exact kernel is given a relative budget instead.
     bt.deadline_ns = 0ull;  // set by clique launcher when a relative budget is supported
   }
+  // unknown scale (Params default): TLS over the K TIM ratios first (registration.cc:603 -> :410-425)
+  constexpr int kMaxScaleN = 1500;  // single-CTA sort + sequential sweep; larger K needs the sort/scan formulation
+  bt.scale_mode = p.estimate_scaling ? 1 : 0;
+  double *scx = nullptr, *scr = nullptr, *sckey = nullptr;
+  int32_t* scidx = nullptr;
+  long long sc_npad = 0;
+  if (bt.scale_mode) {
+    if (bt.n > kMaxScaleN) {
+      ctx->last_error = "estimate_scaling=true is limited to n <= 1500 on the GPU path in this round";
+      return TZR_ERR_TOO_LARGE;
+    }
+    if (mode == 3) {
+      // reference still runs the scale solver when inlier selection is NONE; supported below
+    }
+    const long long K = (long long)bt.n * (bt.n - 1) / 2;
+    sc_npad = 1;
+    while (sc_npad < 2 * K) sc_npad <<= 1;
+    int rc;
+    if ((rc = ensure(ctx, ctx->sc_x, (size_t)bt.B * K * 8 + 8)) != TZR_OK) return rc;
+    if ((rc = ensure(ctx, ctx->sc_r, (size_t)bt.B * K * 8 + 8)) != TZR_OK) return rc;
+    if ((rc = ensure(ctx, ctx->sc_key, (size_t)bt.B * sc_npad * 8)) != TZR_OK) return rc;
+    if ((rc = ensure(ctx, ctx->sc_idx, (size_t)bt.B * sc_npad * 4)) != TZR_OK) return rc;
+    scx = (double*)ctx->sc_x.p;
+    scr = (double*)ctx->sc_r.p;
+    sckey = (double*)ctx->sc_key.p;
+    scidx = (int32_t*)ctx->sc_idx.p;
+  }
   cudaEventRecord(ctx->ev[0], st);
   init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(bt.sol, bt.B);
   if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
   launch_prep(bt, st);
-  cudaEventRecord(ctx->ev[1], st);
   ctx->launches += 2;
+  if (bt.scale_mode) ctx->launches += launch_scale_estimation(bt, scx, scr, sckey, scidx, sc_npad, st);
+  cudaEventRecord(ctx->ev[1], st);
   int nl = 0;
   if (mode != 3) {
     launch_graph(bt, st);
@@ -335,7 +359,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
-                    &ctx->misc};
+                    &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);

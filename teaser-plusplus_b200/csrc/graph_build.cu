@@ -24,17 +24,9 @@
 namespace tzr {
 
 // ------------------------------------------------------------------------------------------------
-// exact predicate: the reference's operation sequence in IEEE double, no contraction
+// exact predicate (tim_norm_exact lives in tzr_internal.cuh): the reference's operation sequence in IEEE
+// double, no contraction
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double tim_norm_exact(const double* __restrict__ p, int i, int j) {
-  const double dx = __dsub_rn(p[3 * j + 0], p[3 * i + 0]);
-  const double dy = __dsub_rn(p[3 * j + 1], p[3 * i + 1]);
-  const double dz = __dsub_rn(p[3 * j + 2], p[3 * i + 2]);
-  // src.array().square().colwise().sum(): (x^2 + y^2) + z^2   (registration.cc:434-437)
-  const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-  return __dsqrt_rn(s);
-}
-
 // Deliberately NOT inlined: the exact path runs for ~1e-4 of the pairs; keeping its two DSQRT expansions out
 // of the unrolled sweep keeps the hot loop small enough for the instruction cache.
 __device__ __noinline__ bool edge_exact(const double* __restrict__ src, const double* __restrict__ dst, int i,
@@ -42,6 +34,17 @@ __device__ __noinline__ bool edge_exact(const double* __restrict__ src, const do
   const double d1 = tim_norm_exact(src, i, j);
   const double d2 = tim_norm_exact(dst, i, j);
   return fabs(__dsub_rn(d1, d2)) <= beta;  // (v1_dist - v2_dist).abs() <= beta   registration.cc:442
+}
+
+// Unknown-scale predicate (TLSScaleSolver, registration.cc:410-425 + :86): the pair is an inlier iff
+// | d2/d1 - s_hat | <= beta * (1/d1), with s_hat the TLS scale estimate.
+__device__ __noinline__ bool edge_exact_scale(const double* __restrict__ src, const double* __restrict__ dst, int i,
+                                              int j, double beta, double s_hat) {
+  const double d1 = tim_norm_exact(src, i, j);
+  const double d2 = tim_norm_exact(dst, i, j);
+  const double ratio = __ddiv_rn(d2, d1);
+  const double alpha = __dmul_rn(beta, __ddiv_rn(1.0, d1));
+  return fabs(__dsub_rn(ratio, s_hat)) <= alpha;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -123,7 +126,8 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     const double delta = 256.0 * u32 * (Ms + Md + beta);
     const double gam1 = beta - delta, gam2 = beta + delta;
     const double up = 1.0 + 9.5367431640625e-07, dn = 1.0 - 9.5367431640625e-07;  // 1 +- 2^-20
-    int use64 = anybad || !(Ms < 1e8) || !(Md < 1e8) || !(gam2 > 1e-8) || !isfinite(beta) || (bt.flags_dbg & 1u);
+    int use64 = anybad || !(Ms < 1e8) || !(Md < 1e8) || !(gam2 > 1e-8) || !isfinite(beta) || (bt.flags_dbg & 1u) ||
+                bt.scale_mode;  // unknown-scale predicate: exact path for every pair (FP32 filter: later round)
     if (gam1 > 0) {
       gc.c1 = (float)(2.0 * gam1 * gam1 * dn);
       gc.g1 = (float)(gam1 * gam1 * gam1 * gam1 * up);
@@ -187,8 +191,6 @@ __device__ __forceinline__ PairEval classify(const float4 is, const float4 id, c
   return e;
 }
 
-constexpr int kGraphWarps = kGraphThreads / 32;  // 4
-
 template <bool kVerify>
 __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) {
   const int b = blockIdx.y;
@@ -210,6 +212,8 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
   const GraphConsts* gcp = bt.gc + b;
   const float c1 = gcp->c1, g1 = gcp->g1, c2 = gcp->c2, g2 = gcp->g2, smin = gcp->smin;
   const double beta = gcp->beta;
+  const bool scale_mode = bt.scale_mode != 0;
+  const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
 
   const float4* sf = bt.sf + (size_t)b * n;
   const float4* df = bt.df + (size_t)b * n;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
       const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
       bool ex = false;
       if (!e.decided && vj[c] && j != i) {
-        ex = edge_exact(src, dst, i, j, beta);
+        ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
         ++nre;
       }
       const uint32_t mex = __ballot_sync(0xffffffffu, ex);

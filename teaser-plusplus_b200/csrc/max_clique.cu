@@ -232,6 +232,24 @@ __global__ void __launch_bounds__(kHeurThreads) clique_heur_kernel(Batch bt) {
     }
     best = block_max_u64(best, s_key);  // contains __syncthreads
     if (s_nuni == cnt) break;           // P was a clique
+    // ---- thinning: candidates whose in-P degree is below half of the best one are dropped at once (they
+    // linger otherwise, because the max-degree pivot rule favours vertices adjacent to them); only when
+    // nothing can be dropped does the pivot join and P shrink to its neighbourhood.
+    const int maxd = (int)(best >> 32) - 1;  // in-P degree of the pivot
+    const int thr = (maxd + 1) / 2;
+    __syncthreads();
+    if (tid == 0) s_nuni = 0;
+    __syncthreads();
+    for (int k = tid; k < cnt; k += blockDim.x) {
+      const int d = dl[k];
+      if (d != cnt - 1 && d < thr) {
+        const int u = list[k];
+        atomicAnd(&P[u >> 5], ~(1u << (u & 31)));
+        s_nuni = 1;
+      }
+    }
+    __syncthreads();
+    if (s_nuni) continue;  // thinned: recompute degrees on the smaller P
     const int u = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
     if (tid == 0) {
       const int pos = s_csz;

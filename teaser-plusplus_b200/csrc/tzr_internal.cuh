@@ -36,6 +36,7 @@ struct GraphConsts {
 // Everything the device kernels need to know about one batch (passed by value).
 struct Batch {
   int B;          // problems
+  int scale_mode; // 1: estimate_scaling=true (TLSScaleSolver predicate, scale from sol[b].scale)
   int n;          // correspondences per problem (uniform inside a device batch)
   double beta;    // 2*noise_bound*sqrt(cbar2)  (registration.cc:438)
   const double* src;  // B*n*3
@@ -82,11 +83,23 @@ struct Batch {
   unsigned long long deadline_ns;  // globaltimer deadline for the exact clique search (0 = none)
 };
 
+// ||v_j - v_i|| exactly as the reference computes a TIM norm: IEEE double, no FMA contraction,
+// src.array().square().colwise().sum() summed as (x^2 + y^2) + z^2   (registration.cc:415-418, :434-437)
+__device__ __forceinline__ double tim_norm_exact(const double* __restrict__ p, int i, int j) {
+  const double dx = __dsub_rn(p[3 * j + 0], p[3 * i + 0]);
+  const double dy = __dsub_rn(p[3 * j + 1], p[3 * i + 1]);
+  const double dz = __dsub_rn(p[3 * j + 2], p[3 * i + 2]);
+  const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  return __dsqrt_rn(s);
+}
+
 // kernels (defined in the .cu files) -------------------------------------------------------------
 void launch_prep(const Batch& bt, cudaStream_t st);
 void launch_graph(const Batch& bt, cudaStream_t st);
 void launch_degree(const Batch& bt, cudaStream_t st);
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);
+int launch_scale_estimation(const Batch& bt, double* X, double* Rg, double* key, int32_t* idx, long long npad,
+                            cudaStream_t st);
 void launch_rot_trans(const Batch& bt, const tzr_params& p, int use_clique, cudaStream_t st);
 size_t clique_heur_smem(int n);
 size_t clique_peel_smem(int n);

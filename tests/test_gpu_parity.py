@@ -378,3 +378,73 @@ def test_solve_full_size_c2(ctx):
     g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
     assert np.array_equal(g["clique"], o["clique"]) and np.array_equal(g["clique"], pr["inliers"])
     assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+# ------------------------------------------------------------------ unknown scale (Params default) + golden fixtures
+BENCH_TOL = {1: (1e-5,) * 6, 2: (1e-5,) * 6, 3: (1e-5,) * 6, 4: (1e-5,) * 6, 5: (1e-5,) * 6,
+             6: (1e-2, 1e-2, 2e-2, 1e-5, 1e-3, 1e-3)}  # registration-benchmark.cc:276-374
+
+
+def _load_benchmark(i):
+    d = os.path.join(synth.GOLDEN_DIR, f"benchmark_{i}")
+    src = synth.read_ply_vertices(os.path.join(d, "src.ply"))
+    dst = synth.read_ply_vertices(os.path.join(d, "dst.ply"))
+    nb = [float(l.split(":")[1]) for l in open(os.path.join(d, "parameters.txt")) if l.startswith("Noise Bound")][0]
+    g = {k: np.loadtxt(os.path.join(d, f"{k}.csv"), delimiter=",", ndmin=2)
+         for k in ("R_ref", "R_est", "t_ref", "t_est", "s_ref", "s_est")}
+    return src, dst, nb, g
+
+
+@pytest.mark.parametrize("i", [1, 2, 3, 4, 5, 6])
+def test_benchmark_fixture_gpu(ctx, i):
+    """The reference's end-to-end known-answer fixtures (test/benchmark/registration-benchmark.cc) through the
+    GPU path with the reference's own parameters (estimate_scaling = true, GNC-TLS, cost_thr 1e-12)."""
+    src, dst, nb, g = _load_benchmark(i)
+    kw = dict(noise_bound=nb, cbar2=1.0, estimate_scaling=1, rotation_max_iterations=100, rotation_gnc_factor=1.4,
+              rotation_estimation_algorithm=0, rotation_cost_threshold=1e-12)
+    out = ctx.solve(src, dst, capi.default_params(**kw))
+    o = orc.solve(src, dst, orc.default_params(**kw))
+    tol = BENCH_TOL[i]
+    assert out["valid"]
+    assert abs(out["scale"] - g["s_ref"].item()) <= tol[0]
+    assert synth.angular_error(g["R_ref"], out["R"]) <= tol[1]
+    assert np.linalg.norm(out["t"] - g["t_ref"].ravel()) <= tol[2]
+    assert abs(out["scale"] - g["s_est"].item()) <= tol[3]
+    assert synth.angular_error(g["R_est"], out["R"]) <= tol[4]
+    assert np.linalg.norm(out["t"] - g["t_est"].ravel()) <= tol[5]
+    # and against the oracle on identical inputs
+    assert np.array_equal(out["clique"], o["clique"])
+    assert abs(out["scale"] - o["scale"]) <= 1e-12
+    assert synth.angular_error(o["R"], out["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - out["t"]) <= TRANS_TOL
+
+
+def test_unknown_scale_object_scene(ctx):
+    d = os.path.join(synth.GOLDEN_DIR, "registration_test")
+    obj = np.loadtxt(os.path.join(d, "objectIn.csv"), delimiter=",").T
+    scene = np.loadtxt(os.path.join(d, "sceneIn.csv"), delimiter=",").T
+    kw = dict(noise_bound=0.0067364, estimate_scaling=1, rotation_cost_threshold=1e-12)
+    g = ctx.solve(obj, scene, capi.default_params(**kw))
+    o = orc.solve(obj, scene, orc.default_params(**kw))
+    assert abs(g["scale"] - 0.955885) < 1e-4  # registration-test.cc:313
+    assert abs(g["scale"] - o["scale"]) <= 1e-12
+    assert np.array_equal(g["clique"], o["clique"])
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+@pytest.mark.parametrize("scale", [0.5, 1.0, 2.7])
+def test_unknown_scale_synthetic(ctx, scale):
+    pr = synth.config_problem("C4", 4, n=500)
+    dst = pr["dst"] * scale
+    kw = dict(noise_bound=pr["noise_bound"] * scale, estimate_scaling=1, rotation_cost_threshold=1e-12)
+    g = ctx.solve(pr["src"], dst, capi.default_params(**kw))
+    o = orc.solve(pr["src"], dst, orc.default_params(**kw))
+    assert abs(g["scale"] - o["scale"]) <= 1e-10 and abs(g["scale"] - scale) < 0.02 * scale
+    assert np.array_equal(g["clique"], o["clique"])
+    assert g["n_edges"] == o["sol"].n_edges
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+def test_unknown_scale_too_large_is_loud(ctx):
+    pr = synth.config_problem("C2", 0, n=1600)
+    with pytest.raises(capi.TzrError):
+        ctx.solve(pr["src"], pr["dst"], capi.default_params(noise_bound=pr["noise_bound"], estimate_scaling=1))
