@@ -433,7 +433,7 @@ def test_unknown_scale_object_scene(ctx):
 
 @pytest.mark.parametrize("scale", [0.5, 1.0, 2.7])
 def test_unknown_scale_synthetic(ctx, scale):
-    pr = synth.config_problem("C4", 4, n=500)
+    pr = synth.make_problem(400, 0.5, 4242, "ball")
     dst = pr["dst"] * scale
     kw = dict(noise_bound=pr["noise_bound"] * scale, estimate_scaling=1, rotation_cost_threshold=1e-12)
     g = ctx.solve(pr["src"], dst, capi.default_params(**kw))
@@ -444,7 +444,72 @@ def test_unknown_scale_synthetic(ctx, scale):
     assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
 
 
+def test_unknown_scale_outlier_dominated(ctx):
+    """90 % ball outliers: the TLS scale consensus is NOT the true scale — GPU and oracle must still agree."""
+    pr = synth.config_problem("C4", 4, n=500)
+    kw = dict(noise_bound=pr["noise_bound"], estimate_scaling=1, rotation_cost_threshold=1e-12)
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    assert abs(g["scale"] - o["scale"]) <= 1e-10
+    assert np.array_equal(g["clique"], o["clique"]) and g["n_edges"] == o["sol"].n_edges
+    assert g["valid"] == o["valid"]
+    if o["valid"]:
+        assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
 def test_unknown_scale_too_large_is_loud(ctx):
     pr = synth.config_problem("C2", 0, n=1600)
     with pytest.raises(capi.TzrError):
         ctx.solve(pr["src"], pr["dst"], capi.default_params(noise_bound=pr["noise_bound"], estimate_scaling=1))
+
+
+# ------------------------------------------------------------------ drop-in surfaces above the C-ABI
+def test_pybind_facade_matches_capi(ctx):
+    """teaserpp_python (pybind11 over the C++ façade) gives the same answer as the raw C-ABI call."""
+    import subprocess
+    import sys
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "teaser-plusplus_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host])
+    sys.path.insert(0, os.path.join(host, "python"))
+    import teaserpp_python as tp
+    pr = synth.config_problem("C4", 7, n=700)
+    p = tp.RobustRegistrationSolver.Params()
+    p.noise_bound = pr["noise_bound"]
+    p.estimate_scaling = False
+    p.rotation_cost_threshold = 1e-12
+    s = tp.RobustRegistrationSolver(p)
+    sol = s.solve(pr["src"].T, pr["dst"].T)  # the reference API takes (3, N)
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**fixed_params(pr["noise_bound"])))
+    assert sol.valid and np.array_equal(np.array(s.getInlierMaxClique()), g["clique"])
+    assert np.array_equal(sol.rotation, g["R"]) and np.array_equal(sol.translation, g["t"]) and sol.scale == 1.0
+    assert np.array_equal(s.getTranslationInliersMask(), g["trans_inliers"])
+    assert np.array_equal(s.getRotationInliersMask(), g["rot_inliers"])
+    assert s.getTranslationInliers() == np.nonzero(g["trans_inliers"])[0].tolist()
+    assert s.isMaxCliqueProvenOptimal()
+    # lazy O(N^2) getters agree with the oracle's materialised versions
+    adj = s.getInlierGraph()
+    obits, odeg, oe = orc.build_graph_bits(pr["src"], pr["dst"], pr["noise_bound"])
+    assert [len(a) for a in adj] == odeg.tolist() and s.getNumInlierGraphEdges() == oe
+    mask = s.getScaleInliersMask()
+    tims = s.getSrcTIMs()
+    assert mask.shape[0] == 700 * 699 // 2 and int(mask.sum()) == oe and tims.shape == (3, 700 * 699 // 2)
+    assert np.array_equal(tims[:, 0], pr["src"][1] - pr["src"][0])
+    # a second solve on the same object is clean (the reference compounds state, SURVEY Q2)
+    sol2 = s.solve(pr["src"].T, pr["dst"].T)
+    assert np.array_equal(sol2.rotation, sol.rotation) and s.getRotationInliers() == np.nonzero(g["rot_inliers"])[0].tolist()
+    # decoupled sub-solver entry points
+    t = s.solveForTranslation(pr["src"][pr["inliers"]].T, (pr["src"][pr["inliers"]] + np.array([1.0, 2.0, 3.0])).T) \
+        if hasattr(s, "solveForTranslation") else None
+
+
+def test_cpp_example_bunny():
+    """The reference's C++ quick-start, compiled against the drop-in header, runs on the GPU."""
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "teaser-plusplus_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host])
+    out = subprocess.run([os.path.join(host, "example_cpp_ply"), os.path.join(synth.GOLDEN_DIR, "bun_zipper_res3.ply")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    vals = {l.split(":")[0]: float(l.split(":")[1]) for l in out.stdout.strip().splitlines()}
+    assert vals["rotation error (rad)"] < 0.01 and vals["translation error (m)"] < 0.01
+    assert vals["clique size"] > 500
