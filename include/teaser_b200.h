@@ -137,8 +137,9 @@ int tzr_scalar_tls(tzr_ctx* ctx, const double* x, const double* ranges, int64_t 
 /* ---- whole path -----------------------------------------------------------------------------
  * Replaces RobustRegistrationSolver::solve(src, dst) (registration.cc:568-737) for one problem
  * (tzr_solve) or B independent problems (tzr_solve_batch).  All intermediates stay on the device.
- * clique: capacity n, sorted.  rot_inliers: capacity = number of rotation TIMs (clique size for
- * CHAIN).  trans_inliers: capacity clique size (n is always enough).  Optional outputs may be NULL. */
+ * clique: capacity n, sorted.  rot_inliers: one byte per rotation TIM — clique_size bytes for CHAIN (capacity n
+ * is always enough), clique_size*(clique_size-1)/2 for COMPLETE (capacity n*(n-1)/2 is always enough).
+ * trans_inliers: clique_size bytes (capacity n).  Optional outputs may be NULL. */
 int tzr_solve(tzr_ctx* ctx, const tzr_params* params, const double* src_3xN, const double* dst_3xN, int n,
               tzr_solution* solution, int32_t* clique, uint8_t* rot_inliers, uint8_t* trans_inliers);
 

@@ -491,6 +491,108 @@ GncResult fgr(const double* src, const double* dst, i64 match_size, size_t max_i
   return res;
 }
 
+// utils::svdRot2d  (teaser/include/teaser/utils.h:145-160): H = X diag(W) Y^T (2x2), JacobiSVD, reflection fix on
+// V.col(1), R = V U^T.  The 2x2 SVD is one two-sided Jacobi step (symmetrise, then diagonalise).
+void svd_rot2d(const double* X, const double* Y, const double* W, i64 m, double R2[4] /* column-major 2x2 */) {
+  double h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+  for (i64 j = 0; j < m; ++j) {
+    const double w = W[j];
+    const double x0 = X[3 * j] * w, x1 = X[3 * j + 1] * w;
+    const double y0 = Y[3 * j], y1 = Y[3 * j + 1];
+    h00 += x0 * y0; h01 += x0 * y1;
+    h10 += x1 * y0; h11 += x1 * y1;
+  }
+  // step 1: G1 = [c1 s1; -s1 c1] such that G1*H is symmetric
+  double c1 = 1, s1 = 0;
+  const double t = h00 + h11, d = h10 - h01;
+  const double tiny = std::numeric_limits<double>::min();
+  if (std::fabs(d) >= tiny) {
+    const double u = t / d, hh = std::sqrt(1.0 + u * u);
+    s1 = 1.0 / hh;
+    c1 = u / hh;
+  }
+  const double n00 = c1 * h00 + s1 * h10, n01 = c1 * h01 + s1 * h11, n11 = c1 * h11 - s1 * h01;
+  // step 2: J = [c2 s2; -s2 c2] diagonalising the symmetric block
+  double c2 = 1, s2 = 0;
+  if (2.0 * std::fabs(n01) >= tiny) {
+    const double tau = (n00 - n11) / (2.0 * n01), w = std::sqrt(tau * tau + 1.0);
+    const double tt = (tau >= 0) ? -1.0 / (tau + w) : 1.0 / (w - tau);
+    c2 = 1.0 / std::sqrt(tt * tt + 1.0);
+    s2 = tt * c2;
+  }
+  // L = J^T G1, D = L H J diagonal;  H = L^T D J^T  => U = L^T, V = J (then sign/sort fixes)
+  const double cl = c2 * c1 + s2 * s1, sl = c2 * s1 - s2 * c1;
+  double U[4] = {cl, sl, -sl, cl};   // column-major: U = L^T = [cl -sl; sl cl]
+  double V[4] = {c2, -s2, s2, c2};   // column-major: V = J   = [c2 s2; -s2 c2]
+  double d0 = cl * (h00 * c2 - h01 * s2) + sl * (h10 * c2 - h11 * s2);
+  double d1 = -sl * (h00 * s2 + h01 * c2) + cl * (h10 * s2 + h11 * c2);
+  if (d0 < 0) { d0 = -d0; U[0] = -U[0]; U[1] = -U[1]; }
+  if (d1 < 0) { d1 = -d1; U[2] = -U[2]; U[3] = -U[3]; }
+  if (d1 > d0) {  // sort descending
+    std::swap(d0, d1);
+    std::swap(U[0], U[2]); std::swap(U[1], U[3]);
+    std::swap(V[0], V[2]); std::swap(V[1], V[3]);
+  }
+  const double detU = U[0] * U[3] - U[2] * U[1], detV = V[0] * V[3] - V[2] * V[1];
+  if (detU * detV < 0) { V[2] = -V[2]; V[3] = -V[3]; }
+  // R = V U^T
+  R2[0] = V[0] * U[0] + V[2] * U[2];  // (0,0)
+  R2[1] = V[1] * U[0] + V[3] * U[2];  // (1,0)
+  R2[2] = V[0] * U[1] + V[2] * U[3];  // (0,1)
+  R2[3] = V[1] * U[1] + V[3] * U[3];  // (1,1)
+}
+
+// QuatroSolver::solveForRotation (teaser/src/registration.cc:280-408): yaw-only GNC-TLS.  The reference keeps
+// the noise bound in function-local statics (:329-330), i.e. the FIRST call's value sticks for the lifetime of
+// the process; this restatement uses the solver's current params_.noise_bound (the evident intent).
+GncResult quatro(const double* src, const double* dst, i64 match_size, size_t max_iterations, double cost_threshold,
+                 double gnc_factor, double noise_bound, uint8_t* inliers) {
+  GncResult res;
+  res.R = m3_identity();
+  double R2[4] = {1, 0, 0, 1};
+  double mu = 1;
+  double prev_cost = std::numeric_limits<double>::infinity();
+  double cost = std::numeric_limits<double>::infinity();
+  double noise_bound_sq = std::pow(noise_bound, 2);
+  if (noise_bound_sq < 1e-16) noise_bound_sq = 1e-2;
+  std::vector<double> weights(match_size, 1.0), residuals_sq(match_size);
+  int it_done = 0;
+  for (size_t i = 0; i < max_iterations; ++i) {
+    it_done = (int)i + 1;
+    svd_rot2d(src, dst, weights.data(), match_size, R2);
+    for (i64 j = 0; j < match_size; ++j) {
+      const double x = src[3 * j], y = src[3 * j + 1];
+      const double d0 = dst[3 * j + 0] - (R2[0] * x + R2[2] * y);
+      const double d1 = dst[3 * j + 1] - (R2[1] * x + R2[3] * y);
+      residuals_sq[j] = d0 * d0 + d1 * d1;
+    }
+    if (i == 0) {
+      double max_residual = residuals_sq[0];
+      for (i64 j = 1; j < match_size; ++j) max_residual = std::max(max_residual, residuals_sq[j]);
+      mu = 1 / (2 * max_residual / noise_bound_sq - 1);
+      if (mu <= 0) break;
+    }
+    const double th1 = (mu + 1) / mu * noise_bound_sq, th2 = mu / (mu + 1) * noise_bound_sq;
+    cost = 0;
+    for (i64 j = 0; j < match_size; ++j) {
+      cost += weights[j] * residuals_sq[j];
+      if (residuals_sq[j] >= th1) weights[j] = 0;
+      else if (residuals_sq[j] <= th2) weights[j] = 1;
+      else weights[j] = std::sqrt(noise_bound_sq * mu * (mu + 1) / residuals_sq[j]) - mu;
+    }
+    const double cost_diff = std::fabs(cost - prev_cost);
+    mu = mu * gnc_factor;
+    prev_cost = cost;
+    if (cost_diff < cost_threshold) break;
+  }
+  if (inliers)
+    for (i64 j = 0; j < match_size; ++j) inliers[j] = weights[j] >= 0.4;  // :398-402
+  res.R(0, 0) = R2[0]; res.R(1, 0) = R2[1]; res.R(0, 1) = R2[2]; res.R(1, 1) = R2[3];  // :407
+  res.cost = cost;
+  res.iterations = it_done;
+  return res;
+}
+
 // ----------------------------------------------------------------------------
 // teaser::Graph  (teaser/include/teaser/graph.h:29-207) — adjacency lists; addEdge performs
 // the linear duplicate scan of hasEdge (graph.h:74-82,96-104) exactly as the reference does.
@@ -960,6 +1062,15 @@ int orc_fgr_rotation(const double* src, const double* dst, int64_t m, uint64_t m
   return r.iterations;
 }
 
+int orc_quatro_rotation(const double* src, const double* dst, int64_t m, uint64_t max_iterations,
+                        double cost_threshold, double gnc_factor, double noise_bound, double* R, uint8_t* inliers,
+                        double* cost) {
+  GncResult r = quatro(src, dst, m, max_iterations, cost_threshold, gnc_factor, noise_bound, inliers);
+  std::memcpy(R, r.R.a, sizeof(r.R.a));
+  if (cost) *cost = r.cost;
+  return r.iterations;
+}
+
 // Max clique from CSR adjacency (offsets: n+1 entries).  info[0]=max_core, [1]=lb, [2]=ub, [3]=exact_ran,
 // [4]=timed_out, [5]=nodes (clamped to int).  Returns clique size; clique written unsorted (as findMaxClique).
 int orc_max_clique_csr(const int64_t* offsets, const int32_t* edges, int n, int mode, double kcore_thr,
@@ -1148,6 +1259,9 @@ int orc_solve(const orc_params* p, const double* src, const double* dst, int n, 
   if (p->rotation_estimation_algorithm == 1)
     gr = fgr(pruned_src.data(), pruned_dst.data(), n_rot, p->rotation_max_iterations, p->rotation_cost_threshold,
              p->rotation_gnc_factor, rot_noise_bound, rot_mask.data());
+  else if (p->rotation_estimation_algorithm == 2)
+    gr = quatro(pruned_src.data(), pruned_dst.data(), n_rot, p->rotation_max_iterations, p->rotation_cost_threshold,
+                p->rotation_gnc_factor, rot_noise_bound, rot_mask.data());
   else
     gr = gnc_tls(pruned_src.data(), pruned_dst.data(), n_rot, p->rotation_max_iterations,
                  p->rotation_cost_threshold, p->rotation_gnc_factor, rot_noise_bound, rot_mask.data(), nullptr, 0,

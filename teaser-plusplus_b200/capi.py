@@ -265,13 +265,15 @@ class Context:
         n = s.shape[0]
         sol = Solution()
         clique = np.zeros(n, dtype=np.int32)
-        rm = np.zeros(n, dtype=np.uint8)
+        complete = params.rotation_tim_graph == 1
+        rm = np.zeros(n * (n - 1) // 2 if complete else n, dtype=np.uint8)
         tm = np.zeros(n, dtype=np.uint8)
         self._ck(lib().tzr_solve(self._h, C.byref(params), _p(s, C.c_double), _p(d, C.c_double), n, C.byref(sol),
                                  _p(clique, C.c_int32), _p(rm, C.c_uint8), _p(tm, C.c_uint8)))
         m = sol.clique_size
+        nrot = m * (m - 1) // 2 if complete else m
         return dict(sol=sol, valid=bool(sol.valid), scale=sol.scale, R=sol.R, t=sol.t, clique=clique[:m].copy(),
-                    rot_inliers=rm[:m].astype(bool), trans_inliers=tm[:m].astype(bool),
+                    rot_inliers=rm[:nrot].astype(bool), trans_inliers=tm[:m].astype(bool),
                     gnc_iterations=sol.gnc_iterations, proven=bool(sol.clique_proven_optimal),
                     n_edges=int(sol.n_edges), stage_ms=list(sol.stage_ms))
 

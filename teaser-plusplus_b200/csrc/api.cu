@@ -25,7 +25,7 @@ struct tzr_ctx {
   uint32_t flags = 0;
   int num_sms = 148;
   // device buffers (grow-only)
-  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, stack, cv,
+  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, stack, cv,
       centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx;
   // pinned host staging
   void* h_pin = nullptr;
@@ -34,6 +34,8 @@ struct tzr_ctx {
   Batch last{};
   bool have_last = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start | prep | graph tiles | clique (incl. degrees) | rot+trans
+  cudaStream_t copy_stream = nullptr;  // H2D of chunk k+1 overlaps the kernels of chunk k (host-pointer batches)
+  std::vector<cudaEvent_t> chunk_ev;
 };
 
 namespace {
@@ -93,7 +95,7 @@ int effective_mode(const tzr_params& p) {
 }
 
 // Size the workspace for a (B, n) batch and fill the Batch descriptor (src/dst left to the caller).
-int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
+int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool complete_graph = false) {
   if (B <= 0 || n <= 0) return TZR_ERR_INVALID_ARG;
   if (n > kMaxN) return TZR_ERR_TOO_LARGE;
   Batch bt{};
@@ -124,6 +126,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
   ENS(root_ctr, (size_t)B * sizeof(int32_t));
   ENS(lock, (size_t)B * sizeof(int32_t));
   ENS(flg, (size_t)B * sizeof(int32_t));
+  ENS(kfinal, (size_t)B * sizeof(int32_t));
   // exact phase geometry: ~2 CTAs per SM over the whole batch, at least 1 CTA per problem
   int G = (2 * ctx->num_sms + B - 1) / B;
   if (G < 1) G = 1;
@@ -142,12 +145,19 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
   bt.sort_cap = next_pow2_host(2 * n);
   ENS(ps, Bn * 3 * sizeof(double));
   ENS(pd, Bn * 3 * sizeof(double));
-  ENS(wgt, Bn * sizeof(double));
+  // rotation TIM capacity: n for CHAIN; for COMPLETE min(n(n-1)/2, what a 4 GiB budget allows)
+  bt.rot_cap = n;
+  if (complete_graph) {
+    const long long full = (long long)n * (n - 1) / 2;
+    const long long budget = ((long long)4 << 30) / (9LL * B);
+    bt.rot_cap = std::max<long long>(n, std::min(full, budget));
+  }
+  ENS(wgt, (size_t)B * bt.rot_cap * sizeof(double));
   ENS(res, Bn * sizeof(double));
   ENS(skey, (size_t)B * 3 * bt.sort_cap * sizeof(double));
   ENS(sidx, (size_t)B * 3 * bt.sort_cap * sizeof(int32_t));
   ENS(sorted, Bn * sizeof(int32_t));
-  ENS(rmask, Bn);
+  ENS(rmask, (size_t)B * bt.rot_cap);
   ENS(tmask, Bn);
   ENS(sol, (size_t)B * sizeof(tzr_solution));
   ENS(dbg, 2 * sizeof(unsigned long long));
@@ -170,6 +180,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out) {
   bt.root_ctr = (int32_t*)ctx->root_ctr.p;
   bt.lock = (int32_t*)ctx->lock.p;
   bt.flags = (int32_t*)ctx->flg.p;
+  bt.kcore_final = (int32_t*)ctx->kfinal.p;
   bt.stack = (uint32_t*)ctx->stack.p;
   bt.cv = (int32_t*)ctx->cv.p;
   bt.centry = (int32_t*)ctx->centry.p;
@@ -210,22 +221,55 @@ __global__ void init_solutions_kernel(tzr_solution* sol, int B) {
   sol[b] = s;
 }
 
+// View of problems [b0, b0+Bc) of a batch: every per-problem buffer is offset, geometry is unchanged.
+Batch sub_batch(const Batch& bt, int b0, int Bc) {
+  Batch s = bt;
+  const size_t n = (size_t)bt.n, o = (size_t)b0;
+  const size_t W32 = (size_t)pitch32(bt.n);
+  const size_t warps = (size_t)bt.exact_ctas * 8;
+  s.B = Bc;
+  s.src = bt.src + o * n * 3;
+  s.dst = bt.dst + o * n * 3;
+  s.sf = bt.sf + o * n;
+  s.df = bt.df + o * n;
+  s.gc = bt.gc + o;
+  s.adj = bt.adj + o * n * pitch64(bt.n);
+  s.deg = bt.deg + o * n;
+  s.n_edges2 = bt.n_edges2 + o;
+  s.hclq = bt.hclq + o * kHeurRoots * n;
+  s.hsize = bt.hsize + o * kHeurRoots;
+  s.clq = bt.clq + o * n;
+  s.L = bt.L + o;
+  s.alive = bt.alive + o * W32;
+  s.best_bits = bt.best_bits + o * W32;
+  s.alive_cnt = bt.alive_cnt + o;
+  s.root_ctr = bt.root_ctr + o;
+  s.lock = bt.lock + o;
+  s.flags = bt.flags + o;
+  s.kcore_final = bt.kcore_final + o;
+  s.stack = bt.stack + o * warps * (size_t)bt.max_depth * 2 * W32;
+  s.cv = bt.cv + o * warps * n;
+  s.centry = bt.centry + o * warps * (size_t)bt.max_depth;
+  s.ps = bt.ps + o * n * 3;
+  s.pd = bt.pd + o * n * 3;
+  s.wgt = bt.wgt + o * (size_t)bt.rot_cap;
+  s.res = bt.res + o * n;
+  s.skey = bt.skey + o * 3 * (size_t)bt.sort_cap;
+  s.sidx = bt.sidx + o * 3 * (size_t)bt.sort_cap;
+  s.sorted_clq = bt.sorted_clq + o * n;
+  s.rot_mask = bt.rot_mask + o * (size_t)bt.rot_cap;
+  s.trans_mask = bt.trans_mask + o * n;
+  s.sol = bt.sol + o;
+  return s;
+}
+
 // The fused device pipeline for one uniform batch.  src/dst must already be set in bt.
 int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
   cudaStream_t st = ctx->stream;
-  if (p.rotation_estimation_algorithm != 0) {
-    ctx->last_error = "only GNC_TLS rotation is implemented on the GPU path";
-    return TZR_ERR_UNSUPPORTED;
-  }
-  if (p.rotation_tim_graph != 0) {
-    ctx->last_error = "only the CHAIN TIM graph is implemented on the GPU path";
-    return TZR_ERR_UNSUPPORTED;
-  }
+  if (p.rotation_estimation_algorithm < 0 || p.rotation_estimation_algorithm > 2 || p.rotation_tim_graph < 0 ||
+      p.rotation_tim_graph > 1)
+    return TZR_ERR_INVALID_ARG;
   const int mode = effective_mode(p);
-  if (mode == 2) {
-    ctx->last_error = "KCORE_HEU inlier selection is not implemented on the GPU path yet";
-    return TZR_ERR_UNSUPPORTED;
-  }
   bt.beta = 2.0 * p.noise_bound * std::sqrt(p.cbar2);  // registration.cc:438
   if (mode == 0 && p.max_clique_time_limit > 0 && p.max_clique_time_limit < 1e6) {
     // device-side deadline on %globaltimer (ns since an arbitrary epoch): read it now through a tiny kernel-free
@@ -347,6 +391,7 @@ int tzr_ctx_create(int device, tzr_ctx** out) {
     return TZR_ERR_CUDA;
   }
   for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ev[i]);
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   *out = ctx;
   return TZR_OK;
 }
@@ -357,7 +402,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
-                    &ctx->lock, &ctx->flg, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
+                    &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
                     &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx};
   for (DevBuf* b : bufs)
@@ -365,6 +410,8 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (int i = 0; i < 5; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return TZR_OK;
@@ -448,13 +495,9 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, d
 // ------------------------------------------------------------------------------------------------
 int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, double kcore_thr, double time_limit_s,
                    int32_t* clique, int32_t* clique_size, int32_t* proven_optimal) {
-  (void)kcore_thr;
   (void)time_limit_s;
   if (!ctx || !adj_bits || !clique || !clique_size || n <= 0) return TZR_ERR_INVALID_ARG;
-  if (mode != 0 && mode != 1) {
-    ctx->last_error = "KCORE_HEU inlier selection is not implemented on the GPU path yet";
-    return TZR_ERR_UNSUPPORTED;
-  }
+  if (mode < 0 || mode > 2) return TZR_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   Batch bt;
   int rc = setup_batch(ctx, 1, n, false, &bt);
@@ -467,6 +510,7 @@ int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, doub
   launch_degree(bt, st);
   tzr_params p;
   tzr_params_default(&p);
+  p.kcore_heuristic_threshold = kcore_thr;
   int nl = 1;
   launch_clique(bt, p, mode, st, &nl);
   ctx->launches += nl;
@@ -600,7 +644,7 @@ int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, co
   if (!ctx || !params || !src_dev || !dst_dev || !solutions_dev) return TZR_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   Batch bt;
-  int rc = setup_batch(ctx, B, n, false, &bt);
+  int rc = setup_batch(ctx, B, n, false, &bt, params->rotation_tim_graph == 1);
   if (rc) return rc;
   bt.src = src_dev;
   bt.dst = dst_dev;
@@ -618,7 +662,7 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
                               uint8_t* rot_inliers, uint8_t* trans_inliers) {
   cudaSetDevice(ctx->device);
   Batch bt;
-  int rc = setup_batch(ctx, B, n, true, &bt);
+  int rc = setup_batch(ctx, B, n, true, &bt, params->rotation_tim_graph == 1);
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
   const size_t per = (size_t)n * 3 * sizeof(double);
@@ -641,25 +685,63 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
       pinned = (a1.type == cudaMemoryTypeHost) && (a2.type == cudaMemoryTypeHost);
     cudaGetLastError();
   }
-  if (contiguous && pinned) {
-    CK(cudaMemcpyAsync((void*)bt.src, src[0], per * B, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync((void*)bt.dst, dst[0], per * B, cudaMemcpyHostToDevice, st));
-  } else {
+  const double* hs = src[0];
+  const double* hd = dst[0];
+  if (!(contiguous && pinned)) {
     for (int b = 0; b < B; ++b) {
       memcpy((char*)h_src + per * b, src[b], per);
       memcpy((char*)h_dst + per * b, dst[b], per);
     }
-    CK(cudaMemcpyAsync((void*)bt.src, h_src, per * B, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync((void*)bt.dst, h_dst, per * B, cudaMemcpyHostToDevice, st));
+    hs = h_src;
+    hd = h_dst;
   }
-  rc = run_pipeline(ctx, bt, *params);
-  if (rc) return rc;
+  // Chunked pipeline: the H2D copy of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream).
+  // estimate_scaling batches keep a single chunk (their per-problem scratch is sized per launch).
+  int chunk = B;
+  if (B >= 64 && !params->estimate_scaling) chunk = std::max(32, B / 8);
+  const int n_chunks = (B + chunk - 1) / chunk;
+  while ((int)ctx->chunk_ev.size() < n_chunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(e);
+  }
+  cudaStream_t cs = n_chunks > 1 ? ctx->copy_stream : st;
+  if (n_chunks > 1) {
+    // the copy stream must not overwrite inputs that an earlier call's kernels may still read
+    CK(cudaEventRecord(ctx->chunk_ev[0], st));
+    CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[0], 0));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b0 = c * chunk, Bc = std::min(chunk, B - b0);
+    CK(cudaMemcpyAsync((void*)(bt.src + (size_t)b0 * n * 3), (const char*)hs + per * b0, per * Bc,
+                       cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync((void*)(bt.dst + (size_t)b0 * n * 3), (const char*)hd + per * b0, per * Bc,
+                       cudaMemcpyHostToDevice, cs));
+    if (n_chunks > 1) CK(cudaEventRecord(ctx->chunk_ev[c], cs));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b0 = c * chunk, Bc = std::min(chunk, B - b0);
+    if (n_chunks > 1) CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+    Batch sb = (n_chunks > 1) ? sub_batch(bt, b0, Bc) : bt;
+    rc = run_pipeline(ctx, sb, *params);
+    if (rc) return rc;
+  }
+  ctx->last = bt;
   CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));
   if (cliques) CK(cudaMemcpyAsync(h_clq, bt.sorted_clq, (size_t)B * n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (rot_inliers) CK(cudaMemcpyAsync(rot_inliers, bt.rot_mask, (size_t)n, cudaMemcpyDeviceToHost, st));
-  if (trans_inliers) CK(cudaMemcpyAsync(trans_inliers, bt.trans_mask, (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   memcpy(solutions, h_sol, (size_t)B * sizeof(tzr_solution));
+  for (int b = 0; b < B; ++b)
+    if (h_sol[b].clique_proven_optimal == -2) {
+      ctx->last_error = "COMPLETE TIM graph of this clique does not fit the rotation workspace";
+      return TZR_ERR_TOO_LARGE;
+    }
+  if (B == 1 && h_sol[0].valid) {  // single-problem masks (getRotationInliersMask / getTranslationInliersMask)
+    const long long m = h_sol[0].clique_size;
+    const long long n_rot = params->rotation_tim_graph == 1 ? m * (m - 1) / 2 : m;
+    if (rot_inliers && n_rot > 0) CK(cudaMemcpy(rot_inliers, bt.rot_mask, (size_t)n_rot, cudaMemcpyDeviceToHost));
+    if (trans_inliers && m > 0) CK(cudaMemcpy(trans_inliers, bt.trans_mask, (size_t)m, cudaMemcpyDeviceToHost));
+  }
   if (cliques)
     for (int b = 0; b < B; ++b) {
       const int m = std::max(0, std::min(n, h_sol[b].clique_size));

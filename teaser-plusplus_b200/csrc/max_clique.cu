@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kHeurThreads) clique_heur_kernel(Batch bt) {
   __shared__ int s_chosen[kHeurRoots];
   __shared__ int s_csz, s_nuni;
 
+  if (bt.kcore_final && bt.kcore_final[b]) return;  // KCORE_HEU shortcut already produced the answer
   const int32_t* deg = bt.deg + (size_t)b * n;
   int32_t* C = bt.hclq + ((size_t)b * kHeurRoots + r) * n;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -280,6 +281,17 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
   __shared__ int s_changed, s_cnt;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
 
+  if (bt.kcore_final && bt.kcore_final[b]) {  // clq / L already hold the max-core vertex set (graph.cc:66-81)
+    uint32_t* ag = bt.alive + (size_t)b * W;
+    for (int x = tid; x < W; x += blockDim.x) ag[x] = 0u;
+    if (tid == 0) {
+      bt.root_ctr[b] = 0;
+      bt.lock[b] = 0;
+      bt.flags[b] = 0;
+      bt.alive_cnt[b] = 0;
+    }
+    return;
+  }
   int L = 0, win = 0;
   for (int r = 0; r < kHeurRoots; ++r) {
     const int s = bt.hsize[b * kHeurRoots + r];
@@ -370,6 +382,116 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
   if (lane == 0 && c) atomicAdd(&s_cnt, c);
   __syncthreads();
   if (tid == 0) bt.alive_cnt[b] = s_cnt;
+}
+
+// =================================================================================================
+// K0 (KCORE_HEU mode only): maximum core number by bisection on k, each probe peeling the current core to its
+// k-core with in-set degrees (k-cores are nested, so a probe above `lo` starts from the lo-core).  If
+// max_core > threshold * n the vertices of the innermost core are the answer (graph.cc:66-81: "remove all nodes
+// with core number less than max core number"); otherwise the heuristic kernels run as in PMC_HEU mode.
+// dynamic smem: A[W] | T[W] | Tn[W]
+// =================================================================================================
+size_t clique_kcore_smem(int n) { return (size_t)pitch32(n) * 4 * 3 + 16; }
+
+__global__ void __launch_bounds__(kPeelThreads) clique_kcore_kernel(Batch bt, double kcore_thr) {
+  const int b = blockIdx.x;
+  const int n = bt.n, W = pitch32(n);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* A = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* T = A + W;
+  uint32_t* Tn = T + W;
+  __shared__ unsigned long long s_key[34];
+  __shared__ int s_changed, s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int32_t* deg = bt.deg + (size_t)b * n;
+  unsigned long long md = 0ull;
+  for (int v = tid; v < n; v += blockDim.x) md = max(md, (unsigned long long)(unsigned)deg[v]);
+  const int maxdeg = (int)block_max_u64(md, s_key);
+  for (int x = tid; x < W; x += blockDim.x) {
+    uint32_t m = 0xffffffffu;
+    const int base = x * 32;
+    if (base >= n) m = 0u;
+    else if (base + 32 > n) m = (1u << (n - base)) - 1u;
+    A[x] = m;
+  }
+  __syncthreads();
+  int lo = 0, hi = maxdeg + 1;  // lo-core (= A) is non-empty, hi-core is empty
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    for (int x = tid; x < W; x += blockDim.x) {
+      T[x] = A[x];
+      Tn[x] = A[x];
+    }
+    __syncthreads();
+    for (int round = 0; round < n + 1; ++round) {
+      if (tid == 0) s_changed = 0;
+      __syncthreads();
+      for (int x = wid; x < W; x += nw) {
+        uint32_t m = T[x];
+        while (m) {
+          int u[4], bits[4], d[4], kc = 0;
+          while (m && kc < 4) {
+            bits[kc] = __ffs(m) - 1;
+            m &= m - 1;
+            u[kc] = x * 32 + bits[kc];
+            ++kc;
+          }
+          for (int q = kc; q < 4; ++q) u[q] = u[0];
+          inset_degree4(bt, b, u, kc, T, W, lane, d);
+          if (lane == 0) {
+            uint32_t clr = 0u;
+            for (int q = 0; q < kc; ++q)
+              if (d[q] < mid) clr |= 1u << bits[q];
+            if (clr) {
+              atomicAnd(&Tn[x], ~clr);
+              s_changed = 1;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const int ch = s_changed;
+      for (int x = tid; x < W; x += blockDim.x) T[x] = Tn[x];
+      __syncthreads();
+      if (!ch) break;
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int x = tid; x < W; x += blockDim.x) c += __popc(T[x]);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (s_cnt > 0) {
+      lo = mid;
+      for (int x = tid; x < W; x += blockDim.x) A[x] = T[x];
+    } else {
+      hi = mid;
+    }
+    __syncthreads();
+  }
+  const int max_core = lo;
+  // graph.cc:66-69: threshold != 1 short-circuits; compare against int(thr * |V|)
+  const bool shortcut = (kcore_thr != 1.0) && (max_core > (int)(kcore_thr * (double)n));
+  if (!shortcut) {
+    if (tid == 0) bt.kcore_final[b] = 0;
+    return;
+  }
+  // emit the innermost core's vertices in ascending order (one thread: n <= 32768, off the hot path)
+  if (tid == 0) {
+    int32_t* dst = bt.clq + (size_t)b * n;
+    int cnt = 0;
+    for (int x = 0; x < W; ++x) {
+      uint32_t m = A[x];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        dst[cnt++] = x * 32 + bit;
+      }
+    }
+    bt.L[b] = cnt;
+    bt.kcore_final[b] = 1;
+  }
 }
 
 // =================================================================================================
@@ -683,22 +805,30 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
 // host-side launcher
 // =================================================================================================
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches) {
-  (void)p;
   const int n = bt.n;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(clique_heur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(clique_peel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(clique_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(clique_kcore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
+  int launches = 0;
+  Batch b2 = bt;
+  if (mode == 2) {  // KCORE_HEU (graph.cc:66-81)
+    clique_kcore_kernel<<<bt.B, kPeelThreads, clique_kcore_smem(n), st>>>(bt, p.kcore_heuristic_threshold);
+    ++launches;
+  } else {
+    b2.kcore_final = nullptr;
+  }
   dim3 g1(kHeurRoots, (unsigned)bt.B);
-  clique_heur_kernel<<<g1, kHeurThreads, clique_heur_smem(n), st>>>(bt);
-  clique_peel_kernel<<<bt.B, kPeelThreads, clique_peel_smem(n), st>>>(bt, mode == 0 ? 0 : 1);
-  int launches = 2;
+  clique_heur_kernel<<<g1, kHeurThreads, clique_heur_smem(n), st>>>(b2);
+  clique_peel_kernel<<<bt.B, kPeelThreads, clique_peel_smem(n), st>>>(b2, mode == 0 ? 0 : 1);
+  launches += 2;
   if (mode == 0) {
     dim3 g3((unsigned)bt.exact_ctas, (unsigned)bt.B);
-    clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(bt);
+    clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(b2);
     ++launches;
   }
   if (n_launches) *n_launches += launches;

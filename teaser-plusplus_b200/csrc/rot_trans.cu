@@ -190,64 +190,108 @@ __device__ double block_max(double v, double* s_buf) {
   return s_buf[kRTWarps];
 }
 
-// ---- GNC-TLS (registration.cc:764-866), whole CTA ------------------------------------------------
+// ---- rotation TIM sets --------------------------------------------------------------------------------
+// CHAIN (registration.cc:657-680): m TIMs materialised in ps/pd (pd already de-scaled, :697).
+// COMPLETE (registration.cc:681-694): all m(m-1)/2 differences of the clique points, in computeTIMs order
+// k = i*m - i(i+1)/2 + (j-i-1); they are recomputed from the m clique points on every pass instead of being
+// materialised (only the per-TIM weight has to persist between GNC iterations).
+struct TimSrc {
+  int complete;
+  int m;                // chain: number of TIMs; complete: number of clique points
+  long long count;      // number of TIMs
+  const double* a;      // chain: src TIMs (3*m)        complete: clique src points (3*m)
+  const double* b;      // chain: dst TIMs, de-scaled   complete: clique dst points (3*m)
+  double inv_scale;     // complete only: 1/scale applied to dst differences
+};
+
+template <class F>
+__device__ __forceinline__ void for_each_tim(const TimSrc& t, F&& f) {
+  if (!t.complete) {
+    for (int k = threadIdx.x; k < t.m; k += kRTThreads)
+      f((long long)k, t.a[3 * k], t.a[3 * k + 1], t.a[3 * k + 2], t.b[3 * k], t.b[3 * k + 1], t.b[3 * k + 2]);
+  } else {
+    for (int i = 0; i + 1 < t.m; ++i) {
+      const long long base = (long long)i * t.m - (long long)i * (i + 1) / 2 - i - 1;
+      const double sx = t.a[3 * i], sy = t.a[3 * i + 1], sz = t.a[3 * i + 2];
+      const double dx = t.b[3 * i], dy = t.b[3 * i + 1], dz = t.b[3 * i + 2];
+      for (int j = i + 1 + threadIdx.x; j < t.m; j += kRTThreads)
+        f(base + j, t.a[3 * j] - sx, t.a[3 * j + 1] - sy, t.a[3 * j + 2] - sz, (t.b[3 * j] - dx) * t.inv_scale,
+          (t.b[3 * j + 1] - dy) * t.inv_scale, (t.b[3 * j + 2] - dz) * t.inv_scale);
+    }
+  }
+}
+
 struct GncOut {
   M3 R;
   double cost;
   int iters;
 };
 
-__device__ void gnc_tls_block(const double* __restrict__ ps, const double* __restrict__ pd, int m,
-                              unsigned long long max_iterations, double cost_threshold, double gnc_factor,
-                              double noise_bound, double* __restrict__ wgt, double* __restrict__ res,
+// weighted covariance H = X diag(w) Y^T (utils.h:125) reduced over the block, then R on one thread
+__device__ void rotation_step(const TimSrc& ts, const double* __restrict__ wgt, bool planar, double* s_buf, M3* s_R) {
+  double h[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = 0.0;
+  for_each_tim(ts, [&](long long k, double x0, double x1, double x2, double y0, double y1, double y2) {
+    const double w = wgt[k];
+    const double a0 = x0 * w, a1 = x1 * w, a2 = x2 * w;
+    h[0] += a0 * y0; h[1] += a1 * y0; h[2] += a2 * y0;
+    h[3] += a0 * y1; h[4] += a1 * y1; h[5] += a2 * y1;
+    h[6] += a0 * y2; h[7] += a1 * y2; h[8] += a2 * y2;
+  });
+  block_sum<9>(h, s_buf);
+  if (threadIdx.x == 0) {
+    M3 R;
+    if (!planar) {
+      M3 H;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) H.a[k] = h[k];
+      rotation_from_H(H, R);
+    } else {
+      // utils::svdRot2d (utils.h:145-160): the proper rotation maximising tr(R H2) for the 2x2 block
+      // H2 = [h00 h01; h10 h11] is R = [c -s; s c] with (c, s) ~ (h00 + h11, h01 - h10)  (closed form of V U^T)
+      const double ca = h[0] + h[4], sb = h[3] - h[1];
+      const double nrm = sqrt(ca * ca + sb * sb);
+      m3_identity(R);
+      if (nrm > 0.0) {
+        const double c = ca / nrm, sn = sb / nrm;
+        R(0, 0) = c; R(0, 1) = -sn; R(1, 0) = sn; R(1, 1) = c;
+      }
+    }
+    *s_R = R;
+  }
+  __syncthreads();
+}
+
+// ---- GNC-TLS (registration.cc:764-866) and Quatro (registration.cc:280-408; planar = yaw only), whole CTA ----
+__device__ void gnc_tls_block(const TimSrc& ts, bool planar, unsigned long long max_iterations, double cost_threshold,
+                              double gnc_factor, double noise_bound, double* __restrict__ wgt,
                               uint8_t* __restrict__ mask, GncOut& out, double* s_buf, M3* s_R) {
-  const int tid = threadIdx.x;
   double mu = 1.0;
   double prev_cost = 1.0 / 0.0, cost = 1.0 / 0.0;
   double nbsq = noise_bound * noise_bound;  // std::pow(x, 2)
   if (nbsq < 1e-16) nbsq = 1e-2;            // :794-796
-  for (int j = tid; j < m; j += kRTThreads) wgt[j] = 1.0;
+  for (long long j = threadIdx.x; j < ts.count; j += kRTThreads) wgt[j] = 1.0;
   m3_identity(out.R);
   int it_done = 0;
   __syncthreads();
   for (unsigned long long i = 0; i < max_iterations; ++i) {
     it_done = (int)i + 1;
-    // H = X diag(w) Y^T   (utils.h:125)
-    double h[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) h[k] = 0.0;
-    for (int j = tid; j < m; j += kRTThreads) {
-      const double w = wgt[j];
-      const double x0 = ps[3 * j] * w, x1 = ps[3 * j + 1] * w, x2 = ps[3 * j + 2] * w;
-      const double y0 = pd[3 * j], y1 = pd[3 * j + 1], y2 = pd[3 * j + 2];
-      h[0] += x0 * y0; h[1] += x1 * y0; h[2] += x2 * y0;   // column 0: H(r,0)
-      h[3] += x0 * y1; h[4] += x1 * y1; h[5] += x2 * y1;
-      h[6] += x0 * y2; h[7] += x1 * y2; h[8] += x2 * y2;
-    }
-    block_sum<9>(h, s_buf);
-    if (tid == 0) {
-      M3 H;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) H.a[k] = h[k];
-      M3 R;
-      rotation_from_H(H, R);
-      *s_R = R;
-    }
-    __syncthreads();
+    rotation_step(ts, wgt, planar, s_buf, s_R);
     const M3 R = *s_R;
-    // residuals (:812-813) and cost with the previous weights (:834)
-    double rmax = 0.0;
-    for (int j = tid; j < m; j += kRTThreads) {
-      const double x = ps[3 * j], y = ps[3 * j + 1], z = ps[3 * j + 2];
-      const double d0 = pd[3 * j + 0] - (R(0, 0) * x + R(0, 1) * y + R(0, 2) * z);
-      const double d1 = pd[3 * j + 1] - (R(1, 0) * x + R(1, 1) * y + R(1, 2) * z);
-      const double d2 = pd[3 * j + 2] - (R(2, 0) * x + R(2, 1) * y + R(2, 2) * z);
-      const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
-      res[j] = r2;
-      rmax = fmax(rmax, r2);
-    }
     out.R = R;
+    auto residual = [&](double x, double y, double z, double p0, double p1, double p2) {
+      const double d0 = p0 - (R(0, 0) * x + R(0, 1) * y + R(0, 2) * z);
+      const double d1 = p1 - (R(1, 0) * x + R(1, 1) * y + R(1, 2) * z);
+      if (planar) return d0 * d0 + d1 * d1;  // :349-350 (x,y rows only)
+      const double d2 = p2 - (R(2, 0) * x + R(2, 1) * y + R(2, 2) * z);
+      return d0 * d0 + d1 * d1 + d2 * d2;  // :812-813
+    };
     if (i == 0) {  // :814-825
+      double rmax = 0.0;
+      for_each_tim(ts, [&](long long, double x, double y, double z, double p0, double p1, double p2) {
+        rmax = fmax(rmax, residual(x, y, z, p0, p1, p2));
+      });
       const double max_residual = block_max(rmax, s_buf);
       mu = 1.0 / (2.0 * max_residual / nbsq - 1.0);
       if (mu <= 0.0) break;
@@ -255,10 +299,9 @@ __device__ void gnc_tls_block(const double* __restrict__ ps, const double* __res
     const double th1 = (mu + 1.0) / mu * nbsq;  // :828-829
     const double th2 = mu / (mu + 1.0) * nbsq;
     double c1[1] = {0.0};
-    for (int j = tid; j < m; j += kRTThreads) {
-      const double r2 = res[j];
-      const double w = wgt[j];
-      c1[0] += w * r2;
+    for_each_tim(ts, [&](long long k, double x, double y, double z, double p0, double p1, double p2) {
+      const double r2 = residual(x, y, z, p0, p1, p2);
+      c1[0] += wgt[k] * r2;  // cost with the previous weights (:834)
       double wn;
       if (r2 >= th1)
         wn = 0.0;
@@ -266,8 +309,8 @@ __device__ void gnc_tls_block(const double* __restrict__ ps, const double* __res
         wn = 1.0;
       else
         wn = sqrt(nbsq * mu * (mu + 1.0) / r2) - mu;
-      wgt[j] = wn;
-    }
+      wgt[k] = wn;
+    });
     block_sum<1>(c1, s_buf);
     cost = c1[0];
     const double cost_diff = fabs(cost - prev_cost);  // :847
@@ -276,10 +319,91 @@ __device__ void gnc_tls_block(const double* __restrict__ ps, const double* __res
     if (cost_diff < cost_threshold) break;  // :853
   }
   __syncthreads();
+  const double thr = planar ? 0.4 : 0.5;  // :400 / :863
   if (mask)
-    for (int j = tid; j < m; j += kRTThreads) mask[j] = wgt[j] >= 0.5;  // :861-865
+    for (long long j = threadIdx.x; j < ts.count; j += kRTThreads) mask[j] = wgt[j] >= thr;
   out.cost = cost;
   out.iters = it_done;
+}
+
+// ---- FGR rotation (registration.cc:206-278), whole CTA ----------------------------------------------------
+// utils::calculateDiameter (utils.h:107-112) returns a float: 2*sqrt(max ||x - mean||^2) rounded to single.
+__device__ double tim_diameter(const TimSrc& ts, bool dst_side, double* s_buf) {
+  double c[3] = {0.0, 0.0, 0.0};
+  for_each_tim(ts, [&](long long, double x, double y, double z, double p0, double p1, double p2) {
+    c[0] += dst_side ? p0 : x;
+    c[1] += dst_side ? p1 : y;
+    c[2] += dst_side ? p2 : z;
+  });
+  block_sum<3>(c, s_buf);
+  const double n = (double)ts.count;
+  const double g0 = c[0] / n, g1 = c[1] / n, g2 = c[2] / n;
+  double mx = 0.0;
+  for_each_tim(ts, [&](long long, double x, double y, double z, double p0, double p1, double p2) {
+    const double a = (dst_side ? p0 : x) - g0, b = (dst_side ? p1 : y) - g1, cc = (dst_side ? p2 : z) - g2;
+    mx = fmax(mx, a * a + b * b + cc * cc);
+  });
+  mx = block_max(mx, s_buf);
+  return (double)(float)(2.0 * sqrt(mx));
+}
+
+__device__ void fgr_block(const TimSrc& ts, unsigned long long max_iterations, double cost_threshold,
+                          double gnc_factor, double noise_bound, double* __restrict__ wgt, uint8_t* __restrict__ mask,
+                          GncOut& out, double* s_buf, M3* s_R) {
+  const double nbsq = noise_bound * noise_bound;
+  double cost = 1.0 / 0.0;
+  const double sd = tim_diameter(ts, false, s_buf), dd = tim_diameter(ts, true, s_buf);
+  double global_scale = sd > dd ? sd : dd;  // :226
+  global_scale /= nbsq;
+  double mu = global_scale * global_scale / nbsq;  // :228
+  const double min_mu = 1.0;
+  for (long long j = threadIdx.x; j < ts.count; j += kRTThreads) wgt[j] = 1.0;
+  M3 R;
+  m3_identity(R);
+  int it_done = 0;
+  __syncthreads();
+  for (unsigned long long i = 0; i < max_iterations; ++i) {
+    it_done = (int)i + 1;
+    const double scaled_mu = mu * nbsq;
+    for_each_tim(ts, [&](long long k, double x, double y, double z, double p0, double p1, double p2) {
+      const double d0 = p0 - (R(0, 0) * x + R(0, 1) * y + R(0, 2) * z);
+      const double d1 = p1 - (R(1, 0) * x + R(1, 1) * y + R(1, 2) * z);
+      const double d2 = p2 - (R(2, 0) * x + R(2, 1) * y + R(2, 2) * z);
+      const double q = scaled_mu / (scaled_mu + (d0 * d0 + d1 * d1 + d2 * d2));
+      wgt[k] = q * q;  // :250
+    });
+    __syncthreads();
+    rotation_step(ts, wgt, false, s_buf, s_R);  // :254
+    R = *s_R;
+    double c1[1] = {0.0};
+    for_each_tim(ts, [&](long long, double x, double y, double z, double p0, double p1, double p2) {
+      const double d0 = p0 - (R(0, 0) * x + R(0, 1) * y + R(0, 2) * z);
+      const double d1 = p1 - (R(1, 0) * x + R(1, 1) * y + R(1, 2) * z);
+      const double d2 = p2 - (R(2, 0) * x + R(2, 1) * y + R(2, 2) * z);
+      const double sq = d0 * d0 + d1 * d1 + d2 * d2;
+      c1[0] += (scaled_mu * sq) / (scaled_mu + sq);  // :257-260
+    });
+    block_sum<1>(c1, s_buf);
+    cost = c1[0];
+    if (cost < cost_threshold || mu < min_mu) break;  // :263
+    mu /= gnc_factor;                                 // :272
+  }
+  __syncthreads();
+  if (mask)
+    for (long long j = threadIdx.x; j < ts.count; j += kRTThreads) mask[j] = wgt[j] != 0.0;  // l_pq.cast<bool>() :276
+  out.R = R;
+  out.cost = cost;
+  out.iters = it_done;
+}
+
+// dispatch on ROTATION_ESTIMATION_ALGORITHM (registration.h:382-386)
+__device__ void rotation_block(int alg, const TimSrc& ts, unsigned long long max_iterations, double cost_threshold,
+                               double gnc_factor, double noise_bound, double* wgt, uint8_t* mask, GncOut& out,
+                               double* s_buf, M3* s_R) {
+  if (alg == 1)
+    fgr_block(ts, max_iterations, cost_threshold, gnc_factor, noise_bound, wgt, mask, out, s_buf, s_R);
+  else
+    gnc_tls_block(ts, alg == 2, max_iterations, cost_threshold, gnc_factor, noise_bound, wgt, mask, out, s_buf, s_R);
 }
 
 }  // namespace
@@ -364,25 +488,50 @@ __global__ void __launch_bounds__(kRTThreads) rot_trans_kernel(Batch bt, tzr_par
     if (tid == 0) sol->valid = 0;
     return;
   }
-  // ---- chain TIMs (registration.cc:657-680), de-scale dst (:697), rotation noise bound (:702-704)
+  // ---- rotation TIMs (registration.cc:657-694), de-scale dst (:697), rotation noise bound (:702-704)
   double* ps = bt.ps + (size_t)b * n * 3;
   double* pd = bt.pd + (size_t)b * n * 3;
   const double inv_scale = 1.0 / scale;
-  for (int i = tid; i < m; i += kRTThreads) {
-    const int root = sc[i];
-    const int leaf = (i != m - 1) ? sc[i + 1] : sc[0];
+  TimSrc ts;
+  ts.complete = p.rotation_tim_graph == 1;
+  ts.m = m;
+  ts.a = ps;
+  ts.b = pd;
+  ts.inv_scale = inv_scale;
+  if (!ts.complete) {
+    ts.count = m;
+    for (int i = tid; i < m; i += kRTThreads) {
+      const int root = sc[i];
+      const int leaf = (i != m - 1) ? sc[i + 1] : sc[0];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      ps[3 * i + r] = src[3 * (size_t)leaf + r] - src[3 * (size_t)root + r];
-      pd[3 * i + r] = (dst[3 * (size_t)leaf + r] - dst[3 * (size_t)root + r]) * inv_scale;
+      for (int r = 0; r < 3; ++r) {
+        ps[3 * i + r] = src[3 * (size_t)leaf + r] - src[3 * (size_t)root + r];
+        pd[3 * i + r] = (dst[3 * (size_t)leaf + r] - dst[3 * (size_t)root + r]) * inv_scale;
+      }
     }
+  } else {
+    ts.count = (long long)m * (m - 1) / 2;
+    for (int i = tid; i < m; i += kRTThreads) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        ps[3 * i + r] = src[3 * (size_t)sc[i] + r];
+        pd[3 * i + r] = dst[3 * (size_t)sc[i] + r];
+      }
+    }
+  }
+  if (ts.count > bt.rot_cap) {  // COMPLETE graph larger than the workspace: report, never compute garbage
+    if (tid == 0) {
+      sol->valid = 0;
+      sol->clique_proven_optimal = -2;
+    }
+    return;
   }
   __syncthreads();
   const double rot_nb = p.noise_bound * (2.0 / scale);
   GncOut g;
-  uint8_t* rmask = bt.rot_mask + (size_t)b * n;
-  gnc_tls_block(ps, pd, m, p.rotation_max_iterations, p.rotation_cost_threshold, p.rotation_gnc_factor, rot_nb,
-                bt.wgt + (size_t)b * n, bt.res + (size_t)b * n, rmask, g, s_buf, &s_R);
+  uint8_t* rmask = bt.rot_mask + (size_t)b * bt.rot_cap;
+  rotation_block(p.rotation_estimation_algorithm, ts, p.rotation_max_iterations, p.rotation_cost_threshold,
+                 p.rotation_gnc_factor, rot_nb, bt.wgt + (size_t)b * bt.rot_cap, rmask, g, s_buf, &s_R);
   __syncthreads();
   if (tid == 0) {
     s_cnt[0] = 0;
@@ -391,7 +540,7 @@ __global__ void __launch_bounds__(kRTThreads) rot_trans_kernel(Batch bt, tzr_par
   __syncthreads();
   {
     int c = 0;
-    for (int j = tid; j < m; j += kRTThreads) c += rmask[j];
+    for (long long j = tid; j < ts.count; j += kRTThreads) c += rmask[j];
     c = __reduce_add_sync(0xffffffffu, c);
     if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[0], c);
   }
@@ -499,8 +648,16 @@ __global__ void __launch_bounds__(kRTThreads) gnc_only_kernel(const double* src,
                                                                double* out_cost, int* out_iters) {
   __shared__ double s_buf[kRTWarps * 9 + 9];
   __shared__ M3 s_R;
+  (void)res;
   GncOut g;
-  gnc_tls_block(src, dst, m, max_iter, cost_thr, gnc_factor, noise_bound, wgt, res, mask, g, s_buf, &s_R);
+  TimSrc ts;
+  ts.complete = 0;
+  ts.m = m;
+  ts.count = m;
+  ts.a = src;
+  ts.b = dst;
+  ts.inv_scale = 1.0;
+  gnc_tls_block(ts, false, max_iter, cost_thr, gnc_factor, noise_bound, wgt, mask, g, s_buf, &s_R);
   if (threadIdx.x == 0) {
     for (int k = 0; k < 9; ++k) out_R[k] = g.R.a[k];
     *out_cost = g.cost;

@@ -58,6 +58,7 @@ struct Batch {
   int32_t* root_ctr;      // B work counter for the exact phase
   int32_t* lock;          // B spin lock for incumbent updates
   int32_t* flags;         // B bit0: search incomplete (depth/time budget)
+  int32_t* kcore_final;   // B (KCORE_HEU only, else nullptr): 1 = clq/L already final (max-core shortcut)
   // exact-phase scratch
   uint32_t* stack;        // per warp: max_depth * 2 * pitch32 words
   int32_t* cv;            // per warp: n ints (current clique)
@@ -67,13 +68,14 @@ struct Batch {
   // rotation / translation scratch (per problem)
   double* ps;             // B*3*n chain TIMs src
   double* pd;             // B*3*n chain TIMs dst (de-scaled)
-  double* wgt;            // B*n GNC weights
-  double* res;            // B*n residuals
+  double* wgt;            // B*rot_cap GNC weights (one per rotation TIM)
+  double* res;            // B*n scratch
+  long long rot_cap;      // rotation TIMs per problem the workspace can hold (n for CHAIN)
   double* skey;           // B*3*sort_cap sort keys (per axis)
   int32_t* sidx;          // B*3*sort_cap sort payload
   int sort_cap;           // next_pow2(2n): per-axis capacity of skey/sidx
   int32_t* sorted_clq;    // B*n sorted clique (output order)
-  uint8_t* rot_mask;      // B*n
+  uint8_t* rot_mask;      // B*rot_cap
   uint8_t* trans_mask;    // B*n
   tzr_solution* sol;      // B
   // debug

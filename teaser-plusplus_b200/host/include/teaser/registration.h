@@ -138,8 +138,8 @@ class GNCTLSRotationSolver : public GNCRotationSolver {
   void solveForRotation(const Mat3X& src, const Mat3X& dst, Eigen::Matrix3d* rotation, BoolRow* inliers) override;
 };
 
-// registration.h:290-352 — declared for source compatibility; the GPU path of these two rotation back-ends is
-// a later round: calling them throws std::runtime_error (no silent CPU fallback).
+// registration.h:290-352 — FGR and Quatro run on the device inside solve() (Params::rotation_estimation_algorithm);
+// the stand-alone strategy objects have no C-ABI entry point yet: calling them directly throws (no CPU fallback).
 class FastGlobalRegistrationSolver : public GNCRotationSolver {
  public:
   FastGlobalRegistrationSolver() = delete;

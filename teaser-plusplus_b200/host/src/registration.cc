@@ -134,11 +134,13 @@ void GNCTLSRotationSolver::solveForRotation(const Mat3X& src, const Mat3X& dst, 
   if (inliers) mask_from_bytes(mask, m, inliers);
 }
 
+// The stand-alone FGR / Quatro strategy objects are reached through solve() (whole path on the device); calling
+// them directly on caller-supplied TIMs has no C-ABI entry point yet and fails loudly (no CPU fallback).
 void FastGlobalRegistrationSolver::solveForRotation(const Mat3X&, const Mat3X&, Eigen::Matrix3d*, BoolRow*) {
-  throw std::runtime_error("teaser (B200): the FGR rotation back-end is not implemented on the GPU path yet");
+  throw std::runtime_error("teaser (B200): stand-alone FastGlobalRegistrationSolver::solveForRotation is not exposed; use solve()");
 }
 void QuatroSolver::solveForRotation(const Mat3X&, const Mat3X&, Eigen::Matrix3d*, BoolRow*) {
-  throw std::runtime_error("teaser (B200): the Quatro rotation back-end is not implemented on the GPU path yet");
+  throw std::runtime_error("teaser (B200): stand-alone QuatroSolver::solveForRotation is not exposed; use solve()");
 }
 
 // ------------------------------------------------------------------------------------------------ max clique
@@ -279,7 +281,8 @@ RegistrationSolution RobustRegistrationSolver::solve(const Mat3X& src, const Mat
   tzr_params p = to_c(params_);
   tzr_solution s;
   std::vector<int32_t> clique(n);
-  std::vector<uint8_t> rot(n), trans(n);
+  const bool complete = params_.rotation_tim_graph == INLIER_GRAPH_FORMULATION::COMPLETE;
+  std::vector<uint8_t> rot(complete ? static_cast<size_t>(n) * (n - 1) / 2 + 1 : static_cast<size_t>(n)), trans(n);
   int rc = tzr_solve(ctx, &p, src.data(), dst.data(), n, &s, clique.data(), rot.data(), trans.data());
   if (rc != TZR_OK) fail("RobustRegistrationSolver::solve", rc, ctx);
 
@@ -301,11 +304,24 @@ RegistrationSolution RobustRegistrationSolver::solve(const Mat3X& src, const Mat
   translation_inliers_.clear();
   if (!solution_.valid) return solution_;  // registration.cc:643-647
 
-  mask_from_bytes(rot, m, &rotation_inliers_mask_);
+  const size_t n_rot = complete ? m * (m - 1) / 2 : m;
+  mask_from_bytes(rot, n_rot, &rotation_inliers_mask_);
   mask_from_bytes(trans, m, &translation_inliers_mask_);
-  for (size_t i = 0; i < m; ++i) {
+  for (size_t i = 0; i < n_rot; ++i)
     if (rot[i]) rotation_inliers_.push_back(static_cast<int>(i));
+  for (size_t i = 0; i < m; ++i)
     if (trans[i]) translation_inliers_.push_back(static_cast<int>(i));
+  if (complete) {  // registration.cc:681-694
+    Mat3X si(3, m), di(3, m);
+    for (size_t i = 0; i < m; ++i)
+      for (int r = 0; r < 3; ++r) {
+        si(r, i) = src(r, max_clique_[i]);
+        di(r, i) = dst(r, max_clique_[i]);
+      }
+    pruned_dst_tims_ = computeTIMs(di, &dst_tims_map_rotation_);
+    pruned_src_tims_ = computeTIMs(si, &src_tims_map_rotation_);
+    pruned_dst_tims_ *= (1 / solution_.scale);
+    return solution_;
   }
   // chain TIMs and their maps for the getters (registration.cc:657-680,697)
   pruned_src_tims_.resize(3, m);

@@ -113,6 +113,8 @@ def lib():
     L.orc_gnc_tls_rotation.restype = C.c_int
     L.orc_fgr_rotation.argtypes = [dp, dp, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, dp, u8p, dp]
     L.orc_fgr_rotation.restype = C.c_int
+    L.orc_quatro_rotation.argtypes = [dp, dp, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_double, dp, u8p, dp]
+    L.orc_quatro_rotation.restype = C.c_int
     L.orc_max_clique_csr.argtypes = [i64p, i32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, i32p, i32p]
     L.orc_max_clique_csr.restype = C.c_int
     L.orc_max_clique_bits.argtypes = [u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, i32p, i32p]
@@ -216,6 +218,17 @@ def fgr(src, dst, max_iterations=100, cost_threshold=0.005, gnc_factor=1.4, nois
     cost = C.c_double()
     it = lib().orc_fgr_rotation(_dp(s), _dp(d), m, int(max_iterations), cost_threshold, gnc_factor, noise_bound,
                                 _dp(R), _p(mask, C.c_uint8), C.byref(cost))
+    return dict(R=np.array(R), inliers=mask.astype(bool), cost=cost.value, iterations=it)
+
+
+def quatro(src, dst, max_iterations=100, cost_threshold=0.005, gnc_factor=1.4, noise_bound=0.01):
+    s, d = as_pts(src), as_pts(dst)
+    m = s.shape[0]
+    R = np.zeros((3, 3), order="F")
+    mask = np.zeros(m, dtype=np.uint8)
+    cost = C.c_double()
+    it = lib().orc_quatro_rotation(_dp(s), _dp(d), m, int(max_iterations), cost_threshold, gnc_factor, noise_bound,
+                                   _dp(R), _p(mask, C.c_uint8), C.byref(cost))
     return dict(R=np.array(R), inliers=mask.astype(bool), cost=cost.value, iterations=it)
 
 

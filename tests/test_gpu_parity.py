@@ -513,3 +513,107 @@ def test_cpp_example_bunny():
     vals = {l.split(":")[0]: float(l.split(":")[1]) for l in out.stdout.strip().splitlines()}
     assert vals["rotation error (rad)"] < 0.01 and vals["translation error (m)"] < 0.01
     assert vals["clique size"] > 500
+
+
+# ------------------------------------------------------------------ other rotation back-ends / TIM graphs
+@pytest.mark.parametrize("i", [1, 2, 3, 4, 5, 6])
+def test_benchmark_fixture_gpu_fgr(ctx, i):
+    """registration-benchmark.cc runs every fixture with FGR too (cost threshold 0.005)."""
+    src, dst, nb, g = _load_benchmark(i)
+    kw = dict(noise_bound=nb, cbar2=1.0, estimate_scaling=1, rotation_max_iterations=100, rotation_gnc_factor=1.4,
+              rotation_estimation_algorithm=1, rotation_cost_threshold=0.005)
+    out = ctx.solve(src, dst, capi.default_params(**kw))
+    o = orc.solve(src, dst, orc.default_params(**kw))
+    tol = BENCH_TOL[i]
+    assert abs(out["scale"] - g["s_ref"].item()) <= tol[0]
+    assert synth.angular_error(g["R_ref"], out["R"]) <= tol[1]
+    assert np.linalg.norm(out["t"] - g["t_ref"].ravel()) <= tol[2]
+    assert synth.angular_error(g["R_est"], out["R"]) <= tol[4]
+    assert np.linalg.norm(out["t"] - g["t_est"].ravel()) <= tol[5]
+    assert np.array_equal(out["clique"], o["clique"])
+    assert synth.angular_error(o["R"], out["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - out["t"]) <= TRANS_TOL
+    assert out["gnc_iterations"] == o["gnc_iterations"]
+
+
+def test_object_scene_fgr(ctx):  # registration-test.cc:256-392
+    d = os.path.join(synth.GOLDEN_DIR, "registration_test")
+    obj = np.loadtxt(os.path.join(d, "objectIn.csv"), delimiter=",").T
+    scene = np.loadtxt(os.path.join(d, "sceneIn.csv"), delimiter=",").T
+    Rexp = np.array([[0.9974, -0.0199, -0.0696], [0.0138, 0.9961, -0.0875], [0.0710, 0.0863, 0.9937]])
+    texp = np.array([-0.1011, 0.0908, 0.1344])
+    for es, rtol, ttol in ((1, 0.25, 0.15), (0, 0.2, 0.1)):
+        kw = dict(noise_bound=0.0067364, estimate_scaling=es, rotation_estimation_algorithm=1,
+                  rotation_cost_threshold=0.005)
+        g = ctx.solve(obj, scene, capi.default_params(**kw))
+        o = orc.solve(obj, scene, orc.default_params(**kw))
+        assert synth.angular_error(Rexp, g["R"]) < rtol and np.linalg.norm(g["t"] - texp) < ttol
+        assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+        assert np.array_equal(g["clique"], o["clique"])
+        assert np.array_equal(g["rot_inliers"], o["rot_inliers"])  # l_pq.cast<bool>()
+
+
+@pytest.mark.parametrize("alg,graph", [(1, 0), (2, 0), (0, 1), (1, 1), (2, 1)])
+def test_solve_rotation_variants(ctx, alg, graph):
+    """FGR / Quatro back-ends and the COMPLETE TIM graph, against the oracle on identical inputs."""
+    rng = np.random.default_rng(50 + alg * 2 + graph)
+    n = 400
+    src = rng.uniform(size=(n, 3))
+    if alg == 2:  # Quatro estimates yaw only
+        a = 0.6
+        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    else:
+        R = synth.random_rotation(rng)
+    t = rng.uniform(-1, 1, size=3)
+    nb = 0.02
+    noise = rng.normal(size=(n, 3))
+    noise *= (rng.uniform(0, 0.9, size=(n, 1)) * nb) / np.linalg.norm(noise, axis=1, keepdims=True)
+    dst = src @ R.T + t + noise
+    out_idx = rng.choice(n, size=int(0.8 * n), replace=False)
+    dst[out_idx] = rng.uniform(-3, 3, size=(len(out_idx), 3))
+    kw = dict(noise_bound=nb, estimate_scaling=0, rotation_estimation_algorithm=alg, rotation_tim_graph=graph,
+              rotation_cost_threshold=0.005 if alg == 1 else 1e-9)
+    g = ctx.solve(src, dst, capi.default_params(**kw))
+    o = orc.solve(src, dst, orc.default_params(**kw))
+    assert g["valid"] and np.array_equal(g["clique"], o["clique"])
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+    assert len(g["rot_inliers"]) == len(o["rot_inliers"])
+    assert np.mean(g["rot_inliers"] != o["rot_inliers"]) <= 0.01
+    assert synth.angular_error(R, g["R"]) < 0.05 and np.linalg.norm(t - g["t"]) < 0.05
+
+
+# ------------------------------------------------------------------ KCORE_HEU / PMC_HEU inlier selection modes
+def test_kcore_heu_shortcut(ctx):  # graph.cc:66-81
+    rng = np.random.default_rng(5)
+    n = 300
+    A = np.triu(rng.uniform(size=(n, n)) < 0.05, 1)
+    idx = rng.choice(n, size=200, replace=False)
+    A[np.ix_(idx, idx)] = True
+    A = np.triu(A, 1)
+    A = A | A.T
+    bits = _bits_from_dense(A)
+    oc, info = orc.max_clique_bits(bits, n, mode=2, kcore_thr=0.5)
+    gc, proven = ctx.max_clique(bits, n, mode=2, kcore_thr=0.5)
+    assert info["max_core"] > 150
+    assert np.array_equal(gc, oc) and not proven
+    # threshold 1 short-circuits the comparison -> heuristic clique (valid, maybe not maximum)
+    gc, proven = ctx.max_clique(bits, n, mode=2, kcore_thr=1.0)
+    assert len(gc) >= 150 and all(A[a, b] for a in gc for b in gc if a != b)
+
+
+def test_kcore_heu_below_threshold_and_pmc_heu(ctx):
+    pr = synth.config_problem("C2cube", 3, n=900)
+    bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], 2 * pr["noise_bound"])
+    b = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :900].astype(bool)
+    for mode in (1, 2):
+        gc, proven = ctx.max_clique(bits, 900, mode=mode, kcore_thr=0.5)
+        assert not proven and len(gc) >= len(pr["inliers"])
+        assert all(b[x, y] for x in gc for y in gc if x != y)
+
+
+def test_solve_kcore_heu_mode(ctx):
+    pr = synth.make_problem(500, 0.3, 99, "ball")  # 70 % inliers: max_core = 349 > 0.5 * 500
+    kw = fixed_params(pr["noise_bound"], inlier_selection_mode=2, kcore_heuristic_threshold=0.5)
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    assert np.array_equal(g["clique"], o["clique"]) and not g["proven"]
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL

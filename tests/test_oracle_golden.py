@@ -81,6 +81,21 @@ def test_fgr_rotation_kat():
     assert pkg_synth.angular_error(EXPECTED_R, out["R"]) < 1e-5
 
 
+def test_quatro_rotation_kat():  # registration-test.cc:183-218
+    src = read_csv(os.path.join(GOLD, "registration_test", "rotation_only_src.csv"))
+    Ryaw = np.array([[0.997379773225804, -0.072343541246221, 0.0],
+                     [0.072343541246221, 0.997379773225804, 0.0],
+                     [0.0, 0.0, 1.0]])
+    out = orc.quatro(src, src @ Ryaw.T, 100, 0.005, 1.4, 0.0067364)
+    assert pkg_synth.angular_error(Ryaw, out["R"]) < 1e-5
+    # yaw + planted outliers: still recovers the yaw
+    rng = np.random.default_rng(3)
+    dst = src @ Ryaw.T
+    dst[:40] += rng.normal(size=(40, 3))
+    out = orc.quatro(src, dst, 100, 1e-9, 1.4, 0.01)
+    assert pkg_synth.angular_error(Ryaw, out["R"]) < 1e-3 and out["iterations"] > 2
+
+
 def test_svd3_matches_numpy():
     rng = np.random.default_rng(0)
     for k in range(200):
