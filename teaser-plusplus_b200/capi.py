@@ -294,6 +294,29 @@ class Context:
         cliques = [cl[b, :max(0, int(sols[b]["clique_size"]))].copy() for b in range(B)]
         return sols, cliques
 
+    def solve_batch_array(self, src, dst, params: Params, cliques_out=None, sols_out=None):
+        """Batch of equally sized problems held in two (B, N, 3) float64 C-contiguous arrays (ideally page-locked,
+        e.g. numpy views of torch pinned tensors: the library then DMAs straight from them and overlaps the copy
+        of chunk k+1 with the kernels of chunk k).  No per-problem Python work.
+        Returns (solutions structured array (B,), cliques (B, N) int32 padded, valid prefix = clique_size)."""
+        src = np.asarray(src)
+        dst = np.asarray(dst)
+        if src.dtype != np.float64 or dst.dtype != np.float64 or src.ndim != 3 or src.shape != dst.shape or \
+                src.shape[2] != 3 or not src.flags.c_contiguous or not dst.flags.c_contiguous:
+            raise ValueError("src/dst must be C-contiguous float64 arrays of shape (B, N, 3)")
+        B, n = src.shape[0], src.shape[1]
+        stride = n * 3 * 8
+        sp = (src.ctypes.data + np.arange(B, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
+        dp_ = (dst.ctypes.data + np.arange(B, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
+        ns = np.full(B, n, dtype=np.int32)
+        sols = sols_out if sols_out is not None else np.zeros(B, dtype=SOLUTION_DTYPE)
+        cl = cliques_out if cliques_out is not None else np.empty((B, n), dtype=np.int32)
+        pp = C.POINTER(C.POINTER(C.c_double))
+        self._ck(lib().tzr_solve_batch(self._h, C.byref(params), B, _p(ns, C.c_int32),
+                                       C.cast(sp.ctypes.data, pp), C.cast(dp_.ctypes.data, pp),
+                                       sols.ctypes.data_as(C.POINTER(Solution)), _p(cl, C.c_int32), n))
+        return sols, cl
+
     def solve_batch_dev(self, params: Params, B: int, n: int, src_ptr: int, dst_ptr: int, sol_ptr: int,
                         clique_ptr: int = 0):
         """Device pointers (e.g. torch tensors' data_ptr()); asynchronous on the context's stream."""

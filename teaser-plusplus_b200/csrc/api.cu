@@ -277,27 +277,31 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
     bt.deadline_ns = 0ull;  // set by clique launcher when a relative budget is supported
   }
   // unknown scale (Params default): TLS over the K TIM ratios first (registration.cc:603 -> :410-425)
-  constexpr int kMaxScaleN = 1500;  // single-CTA sort + sequential sweep; larger K needs the sort/scan formulation
+  constexpr int kScaleSmallN = 1500;  // single-CTA bitonic sort + sequential sweep below, sort/scan pipeline above
   bt.scale_mode = p.estimate_scaling ? 1 : 0;
   double *scx = nullptr, *scr = nullptr, *sckey = nullptr;
   int32_t* scidx = nullptr;
   long long sc_npad = 0;
+  const bool scale_large = bt.scale_mode && bt.n > kScaleSmallN;
   if (bt.scale_mode) {
-    if (bt.n > kMaxScaleN) {
-      ctx->last_error = "estimate_scaling=true is limited to n <= 1500 on the GPU path in this round";
-      return TZR_ERR_TOO_LARGE;
-    }
-    if (mode == 3) {
-      // reference still runs the scale solver when inlier selection is NONE; supported below
-    }
     const long long K = (long long)bt.n * (bt.n - 1) / 2;
-    sc_npad = 1;
-    while (sc_npad < 2 * K) sc_npad <<= 1;
     int rc;
-    if ((rc = ensure(ctx, ctx->sc_x, (size_t)bt.B * K * 8 + 8)) != TZR_OK) return rc;
-    if ((rc = ensure(ctx, ctx->sc_r, (size_t)bt.B * K * 8 + 8)) != TZR_OK) return rc;
-    if ((rc = ensure(ctx, ctx->sc_key, (size_t)bt.B * sc_npad * 8)) != TZR_OK) return rc;
-    if ((rc = ensure(ctx, ctx->sc_idx, (size_t)bt.B * sc_npad * 4)) != TZR_OK) return rc;
+    if (!scale_large) {
+      sc_npad = 1;
+      while (sc_npad < 2 * K) sc_npad <<= 1;
+      if ((rc = ensure(ctx, ctx->sc_x, (size_t)bt.B * K * 8 + 8)) != TZR_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sc_r, (size_t)bt.B * K * 8 + 8)) != TZR_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sc_key, (size_t)bt.B * sc_npad * 8)) != TZR_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sc_idx, (size_t)bt.B * sc_npad * 4)) != TZR_OK) return rc;
+    } else {
+      if (2 * K >= (1LL << 31)) {
+        ctx->last_error = "estimate_scaling: 2K end points exceed 2^31";
+        return TZR_ERR_TOO_LARGE;
+      }
+      if ((rc = ensure(ctx, ctx->sc_x, (size_t)K * 8 + 8)) != TZR_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sc_r, (size_t)K * 8 + 8)) != TZR_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sc_key, scale_large_scratch_bytes(bt.n, nullptr))) != TZR_OK) return rc;
+    }
     scx = (double*)ctx->sc_x.p;
     scr = (double*)ctx->sc_r.p;
     sckey = (double*)ctx->sc_key.p;
@@ -306,9 +310,19 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
   cudaEventRecord(ctx->ev[0], st);
   init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(bt.sol, bt.B);
   if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
+  ctx->launches += 1;
+  if (bt.scale_mode) {  // before prep: the FP32 filter copies are pre-scaled by the estimate
+    bt.beta = 2.0 * p.noise_bound * std::sqrt(p.cbar2);
+    if (scale_large) {
+      const int nl2 = launch_scale_estimation_large(bt, scx, scr, sckey, st);
+      if (nl2 < 0) return TZR_ERR_TOO_LARGE;
+      ctx->launches += nl2;
+    } else {
+      ctx->launches += launch_scale_estimation(bt, scx, scr, sckey, scidx, sc_npad, st);
+    }
+  }
   launch_prep(bt, st);
-  ctx->launches += 2;
-  if (bt.scale_mode) ctx->launches += launch_scale_estimation(bt, scx, scr, sckey, scidx, sc_npad, st);
+  ctx->launches += 1;
   cudaEventRecord(ctx->ev[1], st);
   int nl = 0;
   if (mode != 3) {

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
   const double* dst = bt.dst + (size_t)b * n * 3;
   __shared__ double s_red[8][12];
   __shared__ int s_bad[8];
-  __shared__ double s_c[6];
+  __shared__ double s_c[7];
   double mn[6], mx[6];
   for (int k = 0; k < 6; ++k) {
     mn[k] = 1.0 / 0.0;
@@ -121,13 +121,26 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     }
     const double beta = bt.beta;
     gc.beta = beta;
+    // Unknown scale: |d2/d1 - s| <= beta/d1  <=>  |d2 - s*d1| <= beta (d1 > 0), i.e. the fixed-scale test on a
+    // source cloud scaled by s: the float copies are pre-scaled, the exact re-check keeps the reference's
+    // division-based sequence (its rounding differs from the real-number predicate by ~1e-16 relative, far
+    // inside delta).
+    double s_hat = 1.0;
+    if (bt.scale_mode) {
+      s_hat = bt.sol[b].scale;
+      if (!(s_hat > 1e-6) || !(s_hat < 1e6)) {
+        s_hat = 1.0;
+        anybad = 1;  // degenerate estimate: exact path for every pair
+      }
+      Ms *= s_hat;
+    }
+    s_c[6] = s_hat;
     // delta: bound on the FP32 error of |D1 - D2| (<= ~70 u32 (Ms+Md)); 256 u32 (...) used.
     const double u32 = 5.9604644775390625e-08;  // 2^-24
     const double delta = 256.0 * u32 * (Ms + Md + beta);
     const double gam1 = beta - delta, gam2 = beta + delta;
     const double up = 1.0 + 9.5367431640625e-07, dn = 1.0 - 9.5367431640625e-07;  // 1 +- 2^-20
-    int use64 = anybad || !(Ms < 1e8) || !(Md < 1e8) || !(gam2 > 1e-8) || !isfinite(beta) || (bt.flags_dbg & 1u) ||
-                bt.scale_mode;  // unknown-scale predicate: exact path for every pair (FP32 filter: later round)
+    int use64 = anybad || !(Ms < 1e8) || !(Md < 1e8) || !(gam2 > 1e-8) || !isfinite(beta) || (bt.flags_dbg & 1u);
     if (gam1 > 0) {
       gc.c1 = (float)(2.0 * gam1 * gam1 * dn);
       gc.g1 = (float)(gam1 * gam1 * gam1 * gam1 * up);
@@ -147,9 +160,9 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
   float4* df = bt.df + (size_t)b * n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float4 a, c;
-    a.x = (float)(src[3 * i + 0] - s_c[0]);
-    a.y = (float)(src[3 * i + 1] - s_c[1]);
-    a.z = (float)(src[3 * i + 2] - s_c[2]);
+    a.x = (float)((src[3 * i + 0] - s_c[0]) * s_c[6]);
+    a.y = (float)((src[3 * i + 1] - s_c[1]) * s_c[6]);
+    a.z = (float)((src[3 * i + 2] - s_c[2]) * s_c[6]);
     a.w = 0.f;
     c.x = (float)(dst[3 * i + 0] - s_c[3]);
     c.y = (float)(dst[3 * i + 1] - s_c[4]);
@@ -296,7 +309,8 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
       for (int c = 0; c < 4; ++c) {
         const int j = jb + 32 * c;
         const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
-        if (e.decided && vj[c] && j != i) bad += (edge_exact(src, dst, i, j, beta) != e.sure);
+        if (e.decided && vj[c] && j != i)
+          bad += ((scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta)) != e.sure);
       }
       if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
     }

@@ -102,6 +102,8 @@ void launch_degree(const Batch& bt, cudaStream_t st);
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);
 int launch_scale_estimation(const Batch& bt, double* X, double* Rg, double* key, int32_t* idx, long long npad,
                             cudaStream_t st);
+size_t scale_large_scratch_bytes(int n, size_t* cub_temp_bytes);
+int launch_scale_estimation_large(const Batch& bt, double* X, double* Rg, void* scratch, cudaStream_t st);
 void launch_rot_trans(const Batch& bt, const tzr_params& p, int use_clique, cudaStream_t st);
 size_t clique_heur_smem(int n);
 size_t clique_peel_smem(int n);

@@ -361,6 +361,20 @@ def test_solve_batch_matches_single(ctx):
         assert np.array_equal(cliques[b], q["inliers"])
 
 
+def test_solve_batch_array_matches_list_api(ctx):
+    prs = [synth.config_problem("C4", 100 + b, n=400) for b in range(70)]  # >= 64 -> chunked copy/compute overlap
+    src = np.ascontiguousarray(np.stack([q["src"] for q in prs]))
+    dst = np.ascontiguousarray(np.stack([q["dst"] for q in prs]))
+    p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
+    sols, cl = ctx.solve_batch_array(src, dst, p)
+    sols2, cliques2 = ctx.solve_batch([q["src"] for q in prs], [q["dst"] for q in prs], p)
+    for b in range(len(prs)):
+        m = sols[b]["clique_size"]
+        assert np.array_equal(cl[b, :m], cliques2[b]) and np.array_equal(cl[b, :m], prs[b]["inliers"])
+        assert np.array_equal(sols[b]["rotation"], sols2[b]["rotation"])
+        assert np.array_equal(sols[b]["translation"], sols2[b]["translation"])
+
+
 def test_solve_batch_ragged(ctx):
     prs = [synth.config_problem("C2", b, n=n) for b, n in enumerate([200, 333, 64, 500])]
     p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
@@ -457,10 +471,6 @@ def test_unknown_scale_outlier_dominated(ctx):
         assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
 
 
-def test_unknown_scale_too_large_is_loud(ctx):
-    pr = synth.config_problem("C2", 0, n=1600)
-    with pytest.raises(capi.TzrError):
-        ctx.solve(pr["src"], pr["dst"], capi.default_params(noise_bound=pr["noise_bound"], estimate_scaling=1))
 
 
 # ------------------------------------------------------------------ drop-in surfaces above the C-ABI
@@ -616,4 +626,19 @@ def test_solve_kcore_heu_mode(ctx):
     o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
     g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
     assert np.array_equal(g["clique"], o["clique"]) and not g["proven"]
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+def test_unknown_scale_large_n(ctx):
+    """n above the single-CTA limit: radix-sort + deterministic-scan TLS (K = 2 M pairs here)."""
+    pr = synth.make_problem(2000, 0.6, 777, "ball")
+    scale = 1.7
+    dst = pr["dst"] * scale
+    kw = dict(noise_bound=pr["noise_bound"] * scale, estimate_scaling=1, rotation_cost_threshold=1e-12)
+    g = ctx.solve(pr["src"], dst, capi.default_params(**kw))
+    o = orc.solve(pr["src"], dst, orc.default_params(**kw))
+    assert abs(g["scale"] - o["scale"]) <= 1e-9 * scale  # different association of the running sums
+    assert abs(g["scale"] - scale) < 0.02 * scale
+    assert np.array_equal(g["clique"], o["clique"])
+    assert abs(g["n_edges"] - o["sol"].n_edges) <= 2  # a borderline pair may flip with the 1e-13 scale difference
     assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
