@@ -214,6 +214,8 @@ def main():
     clq_d = torch.zeros((B, N_C2), dtype=torch.int32, device="cuda")
     params = solver_params(capi, nb)
     ctx = capi.Context(local_rank)
+    if os.environ.get("TZR_FLAGS"):  # debug / A-B switches of the library (e.g. 8 = previous graph kernel)
+        ctx.set_flags(int(os.environ["TZR_FLAGS"]))
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
 

@@ -353,6 +353,157 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// graph strip kernel (default): same sweep as graph_tile_kernel, but every WARP is independent — it owns 32 rows
+// and walks up to kStripBlocks consecutive 128-column blocks, keeps its 32 row points in a private shared-memory
+// slice (only __syncwarp), and stores its row words (16 B per row) and transposed column words (4 B per row)
+// straight from registers.  No CTA barrier, the row points and the tile decode are amortised over the strip, and
+// a warp waiting for its next column points does not stall its neighbours (ncu on the tile kernel: 12 % of the
+// issue slots were lost at the two __syncthreads of the short-lived CTAs).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStripBlocks = 4;
+
+__host__ __device__ inline int strip_grid(int n) {
+  const int nt = (n + kTile - 1) / kTile;
+  int total = 0;
+  for (int I = 0; I < nt; ++I) total += (nt - I + kStripBlocks - 1) / kStripBlocks;
+  return total;
+}
+
+template <bool kVerify>
+__global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt) {
+  const int b = blockIdx.y;
+  const int n = bt.n;
+  const int nt = (n + kTile - 1) / kTile;
+  int I = 0, p = blockIdx.x;
+  while (true) {
+    const int ng = (nt - I + kStripBlocks - 1) / kStripBlocks;
+    if (p < ng) break;
+    p -= ng;
+    ++I;
+  }
+  const int J0 = I + p * kStripBlocks;
+  const int J1 = min(nt, J0 + kStripBlocks);
+
+  __shared__ float4 s_is[kTile];
+  __shared__ float4 s_id[kTile];
+
+  const GraphConsts* gcp = bt.gc + b;
+  const float c1 = gcp->c1, g1 = gcp->g1, c2 = gcp->c2, g2 = gcp->g2, smin = gcp->smin;
+  const double beta = gcp->beta;
+  const bool scale_mode = bt.scale_mode != 0;
+  const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
+
+  const float4* sf = bt.sf + (size_t)b * n;
+  const float4* df = bt.df + (size_t)b * n;
+  const double* src = bt.src + (size_t)b * n * 3;
+  const double* dst = bt.dst + (size_t)b * n * 3;
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int ibase = I * kTile + 32 * w;
+  const int nrows = min(32, n - ibase);
+  if (nrows <= 0) return;  // whole warp: there is no CTA-level synchronisation in this kernel
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int i = ibase + lane;
+    s_is[tid] = (i < n) ? sf[i] : z4;
+    s_id[tid] = (i < n) ? df[i] : z4;
+  }
+  __syncwarp();
+  uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * pitch32(n);
+  const int P32 = pitch32(n);
+  const uint32_t rmask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
+
+  for (int J = J0; J < J1; ++J) {
+    const int jb = J * kTile + lane;
+    float4 js[4], jd[4];
+    bool vj[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = jb + 32 * c;
+      vj[c] = j < n;
+      js[c] = vj[c] ? sf[j] : z4;
+      jd[c] = vj[c] ? df[j] : z4;
+    }
+    uint32_t roww[4] = {0u, 0u, 0u, 0u}, colw[4] = {0u, 0u, 0u, 0u};
+    uint32_t ambmask = 0u;
+    uint32_t bit = 1u;
+#pragma unroll 2
+    for (int ii = 0; ii < nrows; ++ii, bit <<= 1) {
+      const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
+      bool all_decided = true;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+        all_decided = all_decided && e.decided;
+        const uint32_t m = __ballot_sync(0xffffffffu, e.sure);
+        if (lane == ii) roww[c] = m;
+        colw[c] |= e.sure ? bit : 0u;
+      }
+      if (!__all_sync(0xffffffffu, all_decided)) ambmask |= bit;
+    }
+    // rare: steps with pairs inside the ambiguous band -> exact FP64 sequence for those lanes
+    while (ambmask) {
+      const int ii = __ffs(ambmask) - 1;
+      ambmask &= ambmask - 1;
+      const int i = ibase + ii;
+      const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
+      int nre = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = jb + 32 * c;
+        const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+        bool ex = false;
+        if (!e.decided && vj[c] && j != i) {
+          ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
+          ++nre;
+        }
+        const uint32_t mex = __ballot_sync(0xffffffffu, ex);
+        if (lane == ii) roww[c] |= mex;
+        colw[c] |= ex ? (1u << ii) : 0u;
+      }
+      if (bt.rechecks) {
+        nre = __reduce_add_sync(0xffffffffu, nre);
+        if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
+      }
+    }
+    if (kVerify) {
+      for (int ii = 0; ii < nrows; ++ii) {
+        const int i = ibase + ii;
+        const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
+        int bad = 0;
+        for (int c = 0; c < 4; ++c) {
+          const int j = jb + 32 * c;
+          const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+          if (e.decided && vj[c] && j != i)
+            bad += ((scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta)) !=
+                    e.sure);
+        }
+        if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
+      }
+    }
+    // validity masks (columns >= n, rows >= n, i == j on the diagonal block) and direct stores
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t cm = __ballot_sync(0xffffffffu, vj[c]);
+      roww[c] &= cm;
+      colw[c] = vj[c] ? (colw[c] & rmask) : 0u;
+      if (I == J && c == w) {
+        roww[c] &= ~(1u << lane);
+        colw[c] &= ~(1u << lane);
+      }
+    }
+    if (lane < nrows)
+      *reinterpret_cast<uint4*>(adj32 + (size_t)(ibase + lane) * P32 + 4 * J) =
+          make_uint4(roww[0], roww[1], roww[2], roww[3]);
+    if (I != J) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (vj[c]) adj32[(size_t)(jb + 32 * c) * P32 + 4 * I + w] = colw[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // degree kernel: deg[v] = popcount(row v); n_edges2[b] = sum of degrees.  One warp per row.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) degree_kernel(Batch bt) {
@@ -383,10 +534,18 @@ void launch_prep(const Batch& bt, cudaStream_t st) { prep_kernel<<<bt.B, 256, 0,
 void launch_graph(const Batch& bt, cudaStream_t st) {
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)bt.B);
+  if (bt.flags_dbg & 8u) {  // previous design (one CTA per 128x128 tile, staged through shared memory): A/B only
+    if (bt.flags_dbg & 2u)
+      graph_tile_kernel<true><<<grid, kGraphThreads, 0, st>>>(bt);
+    else
+      graph_tile_kernel<false><<<grid, kGraphThreads, 0, st>>>(bt);
+    return;
+  }
+  dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
   if (bt.flags_dbg & 2u)
-    graph_tile_kernel<true><<<grid, kGraphThreads, 0, st>>>(bt);
+    graph_strip_kernel<true><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else
-    graph_tile_kernel<false><<<grid, kGraphThreads, 0, st>>>(bt);
+    graph_strip_kernel<false><<<sgrid, kGraphThreads, 0, st>>>(bt);
 }
 
 void launch_degree(const Batch& bt, cudaStream_t st) {
