@@ -141,16 +141,9 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     const double gam1 = beta - delta, gam2 = beta + delta;
     const double up = 1.0 + 9.5367431640625e-07, dn = 1.0 - 9.5367431640625e-07;  // 1 +- 2^-20
     int use64 = anybad || !(Ms < 1e8) || !(Md < 1e8) || !(gam2 > 1e-8) || !isfinite(beta) || (bt.flags_dbg & 1u);
-    if (gam1 > 0) {
-      gc.c1 = (float)(2.0 * gam1 * gam1 * dn);
-      gc.g1 = (float)(gam1 * gam1 * gam1 * gam1 * up);
-    } else {
-      gc.c1 = 0.f;
-      gc.g1 = __int_as_float(0x7f800000);  // +inf -> "surely an edge" can never fire
-    }
-    gc.c2 = (float)(2.0 * gam2 * gam2 * up);
-    gc.g2 = (float)(gam2 * gam2 * gam2 * gam2 * dn);
-    gc.smin = use64 ? __int_as_float(0x7f800000) : (float)(16.0 * gam2 * gam2 * up);  // +inf: every pair exact
+    // sure edge: x <= b1; sure non-edge: x > b2.  Exact path for everything: b1 = -1 (x >= 0), b2 = +inf.
+    gc.b1 = (use64 || !(gam1 > 0)) ? -1.0f : (float)(gam1 * dn);
+    gc.b2 = use64 ? __int_as_float(0x7f800000) : (float)(gam2 * up);
     gc.use_fp64 = use64;
     bt.gc[b] = gc;
     bt.n_edges2[b] = 0ull;
@@ -186,21 +179,24 @@ struct PairEval {
   bool sure, decided;
 };
 
+__device__ __forceinline__ float sqrt_approx(float x) {  // one MUFU.SQRT (<= 2 ulp); its error is part of delta
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// FP32 interval classification of one pair:  x = | |ds| - |dd| |  against  beta -/+ delta.
+// 12 FP32 ops for the two squared norms, 2 MUFU.SQRT (their own pipe), 1 FADD, 2 FSETP.
 __device__ __forceinline__ PairEval classify(const float4 is, const float4 id, const float4 js, const float4 jd,
-                                             const float c1, const float g1, const float c2, const float g2,
-                                             const float smin) {
+                                             const float b1, const float b2) {
   const float ax = js.x - is.x, ay = js.y - is.y, az = js.z - is.z;
   const float bx = jd.x - id.x, by = jd.y - id.y, bz = jd.z - id.z;
   const float a = fmaf(az, az, fmaf(ay, ay, ax * ax));
   const float b = fmaf(bz, bz, fmaf(by, by, bx * bx));
-  const float t = a - b, s = a + b;
-  const float tt = t * t;
-  const float r1 = fmaf(c1, s, -g1);
-  const float r2 = fmaf(c2, s, -g2);
+  const float x = fabsf(sqrt_approx(a) - sqrt_approx(b));
   PairEval e;
-  const bool small = s < smin;          // tiny TIMs (and everything, when smin = +inf): always re-checked
-  e.sure = !small && (tt <= r1);        // surely an edge
-  e.decided = e.sure || (!small && (tt > r2));  // ... or surely not an edge
+  e.sure = x <= b1;                 // surely an edge      (b1 = beta - delta, or -1: never)
+  e.decided = e.sure || (x > b2);   // ... or surely not   (b2 = beta + delta, or +inf: never)
   return e;
 }
 
@@ -223,7 +219,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
   __shared__ __align__(16) uint32_t s_col[kTile][4];
 
   const GraphConsts* gcp = bt.gc + b;
-  const float c1 = gcp->c1, g1 = gcp->g1, c2 = gcp->c2, g2 = gcp->g2, smin = gcp->smin;
+  const float b1 = gcp->b1, b2 = gcp->b2;
   const double beta = gcp->beta;
   const bool scale_mode = bt.scale_mode != 0;
   const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
@@ -267,7 +263,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
     bool all_decided = true;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+      const PairEval e = classify(is, id, js[c], jd[c], b1, b2);
       all_decided = all_decided && e.decided;
       const uint32_t m = __ballot_sync(0xffffffffu, e.sure);
       if (lane == ii) roww[c] = m;
@@ -285,7 +281,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int j = jb + 32 * c;
-      const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+      const PairEval e = classify(is, id, js[c], jd[c], b1, b2);
       bool ex = false;
       if (!e.decided && vj[c] && j != i) {
         ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
@@ -308,7 +304,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
       int bad = 0;
       for (int c = 0; c < 4; ++c) {
         const int j = jb + 32 * c;
-        const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+        const PairEval e = classify(is, id, js[c], jd[c], b1, b2);
         if (e.decided && vj[c] && j != i)
           bad += ((scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta)) != e.sure);
       }
@@ -369,6 +365,23 @@ __host__ __device__ inline int strip_grid(int n) {
   return total;
 }
 
+// 32x32 bit transpose across the lanes of a warp: lane l passes row l, receives column l (bit i of the result =
+// bit l of lane i's input).  5 butterfly stages (shuffle + 4 logic ops each).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    const int j = 16 >> st;
+    const uint32_t m = st == 0 ? 0x0000FFFFu : st == 1 ? 0x00FF00FFu : st == 2 ? 0x0F0F0F0Fu : st == 3 ? 0x33333333u
+                                                                                                       : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    if ((lane & j) == 0)
+      x ^= (((x >> j) ^ y) & m) << j;
+    else
+      x ^= ((y >> j) ^ x) & m;
+  }
+  return x;
+}
+
 template <bool kVerify>
 __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt) {
   const int b = blockIdx.y;
@@ -386,9 +399,10 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt)
 
   __shared__ float4 s_is[kTile];
   __shared__ float4 s_id[kTile];
+  __shared__ __align__(16) uint32_t s_rw[kTile][4];  // row words of the current block (warp-private slices)
 
   const GraphConsts* gcp = bt.gc + b;
-  const float c1 = gcp->c1, g1 = gcp->g1, c2 = gcp->c2, g2 = gcp->g2, smin = gcp->smin;
+  const float b1 = gcp->b1, b2 = gcp->b2;
   const double beta = gcp->beta;
   const bool scale_mode = bt.scale_mode != 0;
   const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
@@ -424,24 +438,28 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt)
       js[c] = vj[c] ? sf[j] : z4;
       jd[c] = vj[c] ? df[j] : z4;
     }
-    uint32_t roww[4] = {0u, 0u, 0u, 0u}, colw[4] = {0u, 0u, 0u, 0u};
+    if (nrows < 32) *reinterpret_cast<uint4*>(&s_rw[tid][0]) = make_uint4(0u, 0u, 0u, 0u);  // rows past n stay empty
+    __syncwarp();
+    // ---- hot sweep: 4 pair predicates per lane per step; the four ballots of a step are one uniform 16-byte
+    // shared-memory store (the warp's row words); column words are recovered afterwards by bit transposition
     uint32_t ambmask = 0u;
     uint32_t bit = 1u;
 #pragma unroll 2
     for (int ii = 0; ii < nrows; ++ii, bit <<= 1) {
       const float4 is = s_is[32 * w + ii], id = s_id[32 * w + ii];
       bool all_decided = true;
+      uint32_t m[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+        const PairEval e = classify(is, id, js[c], jd[c], b1, b2);
         all_decided = all_decided && e.decided;
-        const uint32_t m = __ballot_sync(0xffffffffu, e.sure);
-        if (lane == ii) roww[c] = m;
-        colw[c] |= e.sure ? bit : 0u;
+        m[c] = __ballot_sync(0xffffffffu, e.sure);
       }
+      *reinterpret_cast<uint4*>(&s_rw[32 * w + ii][0]) = make_uint4(m[0], m[1], m[2], m[3]);
       if (!__all_sync(0xffffffffu, all_decided)) ambmask |= bit;
     }
-    // rare: steps with pairs inside the ambiguous band -> exact FP64 sequence for those lanes
+    __syncwarp();
+    // ---- rare: steps with pairs inside the ambiguous band -> exact FP64 sequence for those lanes
     while (ambmask) {
       const int ii = __ffs(ambmask) - 1;
       ambmask &= ambmask - 1;
@@ -451,15 +469,14 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int j = jb + 32 * c;
-        const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+        const PairEval e = classify(is, id, js[c], jd[c], b1, b2);
         bool ex = false;
         if (!e.decided && vj[c] && j != i) {
           ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
           ++nre;
         }
         const uint32_t mex = __ballot_sync(0xffffffffu, ex);
-        if (lane == ii) roww[c] |= mex;
-        colw[c] |= ex ? (1u << ii) : 0u;
+        if (lane == 0 && mex) s_rw[32 * w + ii][c] |= mex;
       }
       if (bt.rechecks) {
         nre = __reduce_add_sync(0xffffffffu, nre);
@@ -473,7 +490,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt)
         int bad = 0;
         for (int c = 0; c < 4; ++c) {
           const int j = jb + 32 * c;
-          const PairEval e = classify(is, id, js[c], jd[c], c1, g1, c2, g2, smin);
+          const PairEval e = classify(is, id, js[c], jd[c], b1, b2);
           if (e.decided && vj[c] && j != i)
             bad += ((scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta)) !=
                     e.sure);
@@ -481,16 +498,16 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt)
         if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
       }
     }
-    // validity masks (columns >= n, rows >= n, i == j on the diagonal block) and direct stores
+    __syncwarp();
+    // ---- row words of lane's row; masks (columns >= n, i == j on the diagonal block); transposed column words
+    const uint4 rw = *reinterpret_cast<const uint4*>(&s_rw[tid][0]);
+    uint32_t roww[4] = {rw.x, rw.y, rw.z, rw.w}, colw[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const uint32_t cm = __ballot_sync(0xffffffffu, vj[c]);
       roww[c] &= cm;
-      colw[c] = vj[c] ? (colw[c] & rmask) : 0u;
-      if (I == J && c == w) {
-        roww[c] &= ~(1u << lane);
-        colw[c] &= ~(1u << lane);
-      }
+      if (I == J && c == w) roww[c] &= ~(1u << lane);
+      colw[c] = warp_transpose32(roww[c], lane) & rmask;
     }
     if (lane < nrows)
       *reinterpret_cast<uint4*>(adj32 + (size_t)(ibase + lane) * P32 + 4 * J) =
@@ -500,6 +517,7 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt)
       for (int c = 0; c < 4; ++c)
         if (vj[c]) adj32[(size_t)(jb + 32 * c) * P32 + 4 * I + w] = colw[c];
     }
+    __syncwarp();
   }
 }
 

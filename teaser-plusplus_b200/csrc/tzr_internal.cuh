@@ -25,10 +25,10 @@ constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memo
 
 // Per-problem constants of the FP32 filter (see graph_build.cu).
 struct GraphConsts {
-  float c1, g1;   // sure-edge test:      t^2 <= c1*s - g1        (gamma1 = beta - delta)
-  float c2, g2;   // sure-non-edge test:  t^2 >  c2*s - g2        (gamma2 = beta + delta)
-  float smin;     // pairs with s < smin are always re-checked in FP64
+  float b1;       // x = ||ds| - |dd|| <= b1  : surely an edge      (beta - delta; -1 = never)
+  float b2;       // x > b2                   : surely not an edge  (beta + delta; +inf = never)
   int use_fp64;   // 1: FP32 filter disabled for this problem (range/NaN guard or debug flag)
+  int pad;
   double beta;    // 2*noise_bound*sqrt(cbar2)
   double cs[3], cd[3];  // centres subtracted before the float conversion
 };
