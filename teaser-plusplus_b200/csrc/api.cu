@@ -25,7 +25,7 @@ struct tzr_ctx {
   uint32_t flags = 0;
   int num_sms = 148;
   // device buffers (grow-only)
-  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, stack, cv,
+  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
       centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx;
   // pinned host staging
   void* h_pin = nullptr;
@@ -127,6 +127,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   ENS(lock, (size_t)B * sizeof(int32_t));
   ENS(flg, (size_t)B * sizeof(int32_t));
   ENS(kfinal, (size_t)B * sizeof(int32_t));
+  ENS(tstart, (size_t)B * sizeof(unsigned long long));
   // exact phase geometry: ~2 CTAs per SM over the whole batch, at least 1 CTA per problem
   int G = (2 * ctx->num_sms + B - 1) / B;
   if (G < 1) G = 1;
@@ -181,6 +182,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   bt.lock = (int32_t*)ctx->lock.p;
   bt.flags = (int32_t*)ctx->flg.p;
   bt.kcore_final = (int32_t*)ctx->kfinal.p;
+  bt.t_start = (unsigned long long*)ctx->tstart.p;
   bt.stack = (uint32_t*)ctx->stack.p;
   bt.cv = (int32_t*)ctx->cv.p;
   bt.centry = (int32_t*)ctx->centry.p;
@@ -197,7 +199,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   bt.mismatches = (unsigned long long*)ctx->dbg.p;
   bt.rechecks = (ctx->flags & 4u) ? (unsigned long long*)ctx->dbg.p + 1 : nullptr;
   bt.flags_dbg = ctx->flags;
-  bt.deadline_ns = 0ull;
+  bt.budget_ns = 0ull;
   *out = bt;
   return TZR_OK;
 }
@@ -247,6 +249,7 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
   s.lock = bt.lock + o;
   s.flags = bt.flags + o;
   s.kcore_final = bt.kcore_final + o;
+  s.t_start = bt.t_start + o;
   s.stack = bt.stack + o * warps * (size_t)bt.max_depth * 2 * W32;
   s.cv = bt.cv + o * warps * n;
   s.centry = bt.centry + o * warps * (size_t)bt.max_depth;
@@ -271,11 +274,10 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
     return TZR_ERR_INVALID_ARG;
   const int mode = effective_mode(p);
   bt.beta = 2.0 * p.noise_bound * std::sqrt(p.cbar2);  // registration.cc:438
-  if (mode == 0 && p.max_clique_time_limit > 0 && p.max_clique_time_limit < 1e6) {
-    // device-side deadline on %globaltimer (ns since an arbitrary epoch): read it now through a tiny kernel-free
-    // approximation: the host cannot read globaltimer, so the exact kernel is given a relative budget instead.
-    bt.deadline_ns = 0ull;  // set by clique launcher when a relative budget is supported
-  }
+  // Params::max_clique_time_limit (seconds) -> device-side budget of the exact search
+  bt.budget_ns = 0ull;
+  if (mode == 0 && p.max_clique_time_limit > 0 && p.max_clique_time_limit < 1e7)
+    bt.budget_ns = (unsigned long long)(p.max_clique_time_limit * 1e9);
   // unknown scale (Params default): TLS over the K TIM ratios first (registration.cc:603 -> :410-425)
   constexpr int kScaleSmallN = 1500;  // single-CTA bitonic sort + sequential sweep below, sort/scan pipeline above
   bt.scale_mode = p.estimate_scaling ? 1 : 0;
@@ -416,7 +418,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
-                    &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
+                    &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->tstart, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
                     &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx};
   for (DevBuf* b : bufs)
@@ -509,7 +511,6 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, d
 // ------------------------------------------------------------------------------------------------
 int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, double kcore_thr, double time_limit_s,
                    int32_t* clique, int32_t* clique_size, int32_t* proven_optimal) {
-  (void)time_limit_s;
   if (!ctx || !adj_bits || !clique || !clique_size || n <= 0) return TZR_ERR_INVALID_ARG;
   if (mode < 0 || mode > 2) return TZR_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
@@ -525,6 +526,7 @@ int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, doub
   tzr_params p;
   tzr_params_default(&p);
   p.kcore_heuristic_threshold = kcore_thr;
+  if (mode == 0 && time_limit_s > 0 && time_limit_s < 1e7) bt.budget_ns = (unsigned long long)(time_limit_s * 1e9);
   int nl = 1;
   launch_clique(bt, p, mode, st, &nl);
   ctx->launches += nl;

@@ -382,8 +382,8 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   return x;
 }
 
-template <bool kVerify>
-__global__ void __launch_bounds__(kGraphThreads, 5) graph_strip_kernel(Batch bt) {
+template <bool kVerify, int kMinBlocks>
+__global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip_kernel(Batch bt) {
   const int b = blockIdx.y;
   const int n = bt.n;
   const int nt = (n + kTile - 1) / kTile;
@@ -561,9 +561,13 @@ void launch_graph(const Batch& bt, cudaStream_t st) {
   }
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
   if (bt.flags_dbg & 2u)
-    graph_strip_kernel<true><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    graph_strip_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
+    graph_strip_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else if (bt.flags_dbg & 32u)  // occupancy A/B: 8 CTAs/SM (64 registers)
+    graph_strip_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else
-    graph_strip_kernel<false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    graph_strip_kernel<false, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
 }
 
 void launch_degree(const Batch& bt, cudaStream_t st) {

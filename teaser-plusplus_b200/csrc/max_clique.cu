@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
     bt.root_ctr[b] = 0;
     bt.lock[b] = 0;
     bt.flags[b] = 0;
+    bt.t_start[b] = 0ull;
   }
   // incumbent as a bitset (canonical tie-break in the exact phase compares bitsets)
   {
@@ -715,6 +716,18 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
   c.centry = bt.centry + gw * (size_t)bt.max_depth;
   c.Lp = bt.L + b;
   const uint32_t* alive = bt.alive + (size_t)b * W;
+  // Params::max_clique_time_limit (graph.cc:44): budget counted from the first search warp of this problem
+  unsigned long long deadline = 0ull;
+  if (bt.budget_ns) {
+    unsigned long long t0 = 0ull;
+    if (lane == 0) {
+      const unsigned long long now = globaltimer_ns();
+      const unsigned long long old = atomicCAS(bt.t_start + b, 0ull, now);
+      t0 = old ? old : now;
+    }
+    t0 = __shfl_sync(0xffffffffu, t0, 0);
+    deadline = t0 + bt.budget_ns;
+  }
 
   while (true) {
     int v = 0;
@@ -743,7 +756,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
     while (true) {
       if (fresh) {
         // ---- process the node in Pc
-        if (bt.deadline_ns && (globaltimer_ns() > bt.deadline_ns)) {
+        if (deadline && (globaltimer_ns() > deadline)) {
           if (lane == 0) atomicOr(bt.flags + b, 3);
           depth = 0;
           break;

@@ -82,7 +82,8 @@ struct Batch {
   unsigned long long* mismatches;  // 1
   unsigned long long* rechecks;    // 1
   uint32_t flags_dbg;
-  unsigned long long deadline_ns;  // globaltimer deadline for the exact clique search (0 = none)
+  unsigned long long budget_ns;    // time budget of the exact clique search per problem (0 = none), Params::max_clique_time_limit
+  unsigned long long* t_start;     // B: %globaltimer when the first search warp of the problem started (0 = not yet)
 };
 
 // ||v_j - v_i|| exactly as the reference computes a TIM norm: IEEE double, no FMA contraction,

@@ -642,3 +642,32 @@ def test_unknown_scale_large_n(ctx):
     assert np.array_equal(g["clique"], o["clique"])
     assert abs(g["n_edges"] - o["sol"].n_edges) <= 2  # a borderline pair may flip with the 1e-13 scale difference
     assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+# ------------------------------------------------------------------ full-size stress configs (BASELINE C3 / C5)
+@pytest.mark.parametrize("cfg", ["C3", "C5", "C2cube"])
+def test_solve_full_size_stress(ctx, cfg):
+    """BASELINE configs C3 (N=10000, 99 % in-cube outliers: max-clique stress), C5 (N=8000, 97 %) and the in-cube
+    variant of C2 at full size: identical clique vs the oracle, rotation/translation within tolerance."""
+    pr = synth.config_problem(cfg, 0)
+    kw = fixed_params(pr["noise_bound"])
+    g = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    print(cfg, "gpu stage ms", [round(x, 3) for x in g["stage_ms"][:7]], "clique", len(g["clique"]),
+          "oracle stage ms", [round(x, 1) for x in o["stage_ms"][:7]])
+    assert g["proven"]
+    assert np.array_equal(g["clique"], o["clique"])
+    assert g["n_edges"] == o["sol"].n_edges
+    assert synth.angular_error(o["R"], g["R"]) <= ROT_TOL and np.linalg.norm(o["t"] - g["t"]) <= TRANS_TOL
+
+
+def test_clique_time_limit_is_honoured(ctx):
+    """A tiny max_clique_time_limit stops the exact search: the result is a valid clique, flagged as not proven."""
+    rng = np.random.default_rng(1)
+    n = 600
+    A = np.triu(rng.uniform(size=(n, n)) < 0.5, 1)
+    A = A | A.T
+    bits = _bits_from_dense(A)
+    gc, proven = ctx.max_clique(bits, n, mode=0, time_limit=1e-6)
+    assert not proven and len(gc) >= 2
+    assert all(A[a, b] for a in gc for b in gc if a != b)
