@@ -34,6 +34,8 @@ struct tzr_ctx {
   Batch last{};
   bool have_last = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start | prep | graph tiles | clique (incl. degrees) | rot+trans
+  std::vector<cudaEvent_t> stage_ev;  // 5 per chunk of the last pipelined call (stage timing is summed over chunks)
+  int stage_chunks = 0;
   cudaStream_t copy_stream = nullptr;  // H2D of chunk k+1 overlaps the kernels of chunk k (host-pointer batches)
   std::vector<cudaEvent_t> chunk_ev;
 };
@@ -267,7 +269,7 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
 }
 
 // The fused device pipeline for one uniform batch.  src/dst must already be set in bt.
-int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
+int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev) {
   cudaStream_t st = ctx->stream;
   if (p.rotation_estimation_algorithm < 0 || p.rotation_estimation_algorithm > 2 || p.rotation_tim_graph < 0 ||
       p.rotation_tim_graph > 1)
@@ -309,7 +311,7 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
     sckey = (double*)ctx->sc_key.p;
     scidx = (int32_t*)ctx->sc_idx.p;
   }
-  cudaEventRecord(ctx->ev[0], st);
+  cudaEventRecord(ev[0], st);
   init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(bt.sol, bt.B);
   if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
   ctx->launches += 1;
@@ -325,24 +327,58 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p) {
   }
   launch_prep(bt, st);
   ctx->launches += 1;
-  cudaEventRecord(ctx->ev[1], st);
+  cudaEventRecord(ev[1], st);
   int nl = 0;
   if (mode != 3) {
     launch_graph(bt, st);
-    cudaEventRecord(ctx->ev[2], st);
+    cudaEventRecord(ev[2], st);
     launch_degree(bt, st);
     nl += 2;
     launch_clique(bt, p, mode, st, &nl);
   } else {
-    cudaEventRecord(ctx->ev[2], st);
+    cudaEventRecord(ev[2], st);
   }
-  cudaEventRecord(ctx->ev[3], st);
+  cudaEventRecord(ev[3], st);
   launch_rot_trans(bt, p, mode != 3 ? 1 : 0, st);
-  cudaEventRecord(ctx->ev[4], st);
+  cudaEventRecord(ev[4], st);
   ctx->launches += nl + 1;
+  return check_launch(ctx, "pipeline launch");
+}
+
+// Problems per pipeline chunk: small enough that a chunk's adjacency bitsets (written by the graph kernel, then
+// read by the degree / clique kernels) stay resident in the 126 MB L2 instead of making a round trip through HBM.
+int l2_chunk(const tzr_ctx* ctx, int B, int n, const tzr_params& p) {
+  (void)ctx;
+  if (p.estimate_scaling) return B;  // per-launch scratch of the scale stage
+  const size_t per = (size_t)n * pitch64(n) * 8;
+  long long c = (long long)((size_t)96 << 20) / (long long)std::max<size_t>(per, 1);
+  if (c < 1) c = 1;
+  if (c >= B) return B;
+  return (int)c;
+}
+
+// Run the pipeline chunk by chunk on the compute stream.  ready[c] (optional) is an event the chunk's inputs wait for.
+int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, int chunk, const cudaEvent_t* ready) {
+  const int n_chunks = (bt.B + chunk - 1) / chunk;
+  while ((int)ctx->stage_ev.size() < 5 * n_chunks) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return TZR_ERR_CUDA;
+    ctx->stage_ev.push_back(e);
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b0 = c * chunk, Bc = std::min(chunk, bt.B - b0);
+    if (ready) {
+      if (cudaStreamWaitEvent(ctx->stream, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
+    }
+    Batch sb = (n_chunks > 1) ? sub_batch(bt, b0, Bc) : bt;
+    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * c);
+    if (rc) return rc;
+    if (n_chunks == 1) bt = sb;  // keep fields filled in by run_pipeline (beta, scale_mode, ...)
+  }
+  ctx->stage_chunks = n_chunks;
   ctx->last = bt;
   ctx->have_last = true;
-  return check_launch(ctx, "pipeline launch");
+  return TZR_OK;
 }
 
 }  // namespace
@@ -427,6 +463,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   for (int i = 0; i < 5; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->stage_ev) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -664,7 +701,7 @@ int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, co
   if (rc) return rc;
   bt.src = src_dev;
   bt.dst = dst_dev;
-  rc = run_pipeline(ctx, bt, *params);
+  rc = run_chunked(ctx, bt, *params, l2_chunk(ctx, B, n, *params), nullptr);
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(solutions_dev, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToDevice, st));
@@ -711,12 +748,11 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
     hs = h_src;
     hd = h_dst;
   }
-  // Chunked pipeline: the H2D copy of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream).
-  // estimate_scaling batches keep a single chunk (their per-problem scratch is sized per launch).
-  int chunk = B;
-  if (B >= 64 && !params->estimate_scaling) chunk = std::max(32, B / 8);
+  // Chunked pipeline: the H2D copy of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream);
+  // chunks are L2-sized (see l2_chunk).
+  const int chunk = l2_chunk(ctx, B, n, *params);
   const int n_chunks = (B + chunk - 1) / chunk;
-  while ((int)ctx->chunk_ev.size() < n_chunks) {
+  while ((int)ctx->chunk_ev.size() < n_chunks + 1) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->chunk_ev.push_back(e);
@@ -724,8 +760,8 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
   cudaStream_t cs = n_chunks > 1 ? ctx->copy_stream : st;
   if (n_chunks > 1) {
     // the copy stream must not overwrite inputs that an earlier call's kernels may still read
-    CK(cudaEventRecord(ctx->chunk_ev[0], st));
-    CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[0], 0));
+    CK(cudaEventRecord(ctx->chunk_ev[n_chunks], st));
+    CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[n_chunks], 0));
   }
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = c * chunk, Bc = std::min(chunk, B - b0);
@@ -735,14 +771,8 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
                        cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) CK(cudaEventRecord(ctx->chunk_ev[c], cs));
   }
-  for (int c = 0; c < n_chunks; ++c) {
-    const int b0 = c * chunk, Bc = std::min(chunk, B - b0);
-    if (n_chunks > 1) CK(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
-    Batch sb = (n_chunks > 1) ? sub_batch(bt, b0, Bc) : bt;
-    rc = run_pipeline(ctx, sb, *params);
-    if (rc) return rc;
-  }
-  ctx->last = bt;
+  rc = run_chunked(ctx, bt, *params, chunk, n_chunks > 1 ? ctx->chunk_ev.data() : nullptr);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));
   if (cliques) CK(cudaMemcpyAsync(h_clq, bt.sorted_clq, (size_t)B * n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -773,12 +803,11 @@ int tzr_solve(tzr_ctx* ctx, const tzr_params* params, const double* src, const d
   const double* d[1] = {dst};
   int rc = solve_uniform_host(ctx, params, 1, n, s, d, solution, clique, n, rot_inliers, trans_inliers);
   if (rc) return rc;
-  float ms;
-  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) solution->stage_ms[0] = ms;  // prep
-  if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) solution->stage_ms[1] = ms;  // graph
-  if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) solution->stage_ms[2] = ms;  // clique
-  if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]) == cudaSuccess) solution->stage_ms[3] = ms;  // rot+trans
-  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]) == cudaSuccess) solution->stage_ms[6] = ms;
+  double st4[4] = {0, 0, 0, 0};
+  if (tzr_last_stage_ms(ctx, &st4[0], &st4[1], &st4[2], &st4[3]) == TZR_OK) {
+    for (int i = 0; i < 4; ++i) solution->stage_ms[i] = st4[i];  // prep | graph | clique | rot+trans
+    solution->stage_ms[6] = st4[0] + st4[1] + st4[2] + st4[3];
+  }
   return TZR_OK;
 }
 
@@ -813,13 +842,17 @@ int tzr_last_graph(tzr_ctx* ctx, int b, uint64_t* adj_bits, int32_t* degree) {
 
 int tzr_last_stage_ms(tzr_ctx* ctx, double* prep_ms, double* graph_ms, double* clique_ms, double* rot_trans_ms) {
   if (!ctx || !ctx->have_last) return TZR_ERR_INVALID_ARG;
-  float ms = 0;
+  double acc[4] = {0, 0, 0, 0};
+  for (int c = 0; c < ctx->stage_chunks; ++c)
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->stage_ev[5 * c + i], ctx->stage_ev[5 * c + i + 1]) != cudaSuccess)
+        return TZR_ERR_CUDA;
+      acc[i] += ms;
+    }
   double* outs[4] = {prep_ms, graph_ms, clique_ms, rot_trans_ms};
-  for (int i = 0; i < 4; ++i) {
-    if (!outs[i]) continue;
-    if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) return TZR_ERR_CUDA;
-    *outs[i] = ms;
-  }
+  for (int i = 0; i < 4; ++i)
+    if (outs[i]) *outs[i] = acc[i];
   return TZR_OK;
 }
 

@@ -564,10 +564,10 @@ void launch_graph(const Batch& bt, cudaStream_t st) {
     graph_strip_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
     graph_strip_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else if (bt.flags_dbg & 32u)  // occupancy A/B: 8 CTAs/SM (64 registers)
-    graph_strip_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else
+  else if (bt.flags_dbg & 32u)  // occupancy A/B: 5 CTAs/SM (96 registers)
     graph_strip_kernel<false, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else  // default: 8 CTAs/SM (64 registers, 32 warps/SM) — measured 6 % faster than 5 CTAs/SM (issue-latency bound)
+    graph_strip_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
 }
 
 void launch_degree(const Batch& bt, cudaStream_t st) {

@@ -270,7 +270,72 @@ __global__ void __launch_bounds__(kHeurThreads) clique_heur_kernel(Batch bt) {
 // dynamic smem: A[W32] | Anew[W32]
 // mode: 0 exact, 1 heuristic only
 // =================================================================================================
-size_t clique_peel_smem(int n) { return (size_t)pitch32(n) * 4 * 2 + 16; }
+size_t clique_peel_smem(int n) { return (size_t)pitch32(n) * 4 * 3 + 16; }
+
+namespace {
+
+// One peeling round over the vertices of S (shared-memory bitset): in-set degrees by AND+popcount (one warp per
+// four vertices), optionally stored in dg[]; vertices with degree < thr are cleared in Sn.  Returns via shared
+// counters: s_changed.  Block-wide; contains __syncthreads.
+__device__ void peel_round(const Batch& bt, int b, const uint32_t* S, uint32_t* Sn, int W, int thr, int32_t* dg,
+                           int* s_changed) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  if (tid == 0) *s_changed = 0;
+  __syncthreads();
+  for (int x = wid; x < W; x += nw) {
+    uint32_t m = S[x];  // warp-uniform
+    while (m) {
+      int u[4], bits[4], d[4], kc = 0;
+      while (m && kc < 4) {
+        bits[kc] = __ffs(m) - 1;
+        m &= m - 1;
+        u[kc] = x * 32 + bits[kc];
+        ++kc;
+      }
+      for (int q = kc; q < 4; ++q) u[q] = u[0];
+      inset_degree4(bt, b, u, kc, S, W, lane, d);
+      if (lane == 0) {
+        uint32_t clr = 0u;
+        for (int q = 0; q < kc; ++q) {
+          if (dg) dg[u[q]] = d[q];
+          if (d[q] < thr) clr |= 1u << bits[q];
+        }
+        if (clr) {
+          atomicAnd(&Sn[x], ~clr);
+          *s_changed = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ int block_popcount(const uint32_t* S, int W, int* s_cnt) {
+  const int tid = threadIdx.x;
+  if (tid == 0) *s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int x = tid; x < W; x += blockDim.x) c += __popc(S[x]);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((tid & 31) == 0 && c) atomicAdd(s_cnt, c);
+  __syncthreads();
+  return *s_cnt;
+}
+
+// Peel S in place to its k-core (vertices with >= k neighbours inside the set).  Sn: scratch of W words.
+__device__ void peel_to_core(const Batch& bt, int b, uint32_t* S, uint32_t* Sn, int W, int k, int* s_changed) {
+  for (int x = threadIdx.x; x < W; x += blockDim.x) Sn[x] = S[x];
+  __syncthreads();
+  for (int round = 0; round < 256; ++round) {
+    peel_round(bt, b, S, Sn, W, k, nullptr, s_changed);
+    const int ch = *s_changed;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) S[x] = Sn[x];
+    __syncthreads();
+    if (!ch) break;
+  }
+}
+
+}  // namespace
 
 __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int mode) {
   const int b = blockIdx.x;
@@ -278,8 +343,11 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* A = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* An = A + W;
+  uint32_t* S = An + W;
   __shared__ int s_changed, s_cnt;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  __shared__ unsigned long long s_sum;
+  __shared__ unsigned int s_min;
+  const int tid = threadIdx.x;
 
   if (bt.kcore_final && bt.kcore_final[b]) {  // clq / L already hold the max-core vertex set (graph.cc:66-81)
     uint32_t* ag = bt.alive + (size_t)b * W;
@@ -313,8 +381,8 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
     bt.t_start[b] = 0ull;
   }
   // incumbent as a bitset (canonical tie-break in the exact phase compares bitsets)
+  uint32_t* bb = bt.best_bits + (size_t)b * W;
   {
-    uint32_t* bb = bt.best_bits + (size_t)b * W;
     for (int x = tid; x < W; x += blockDim.x) A[x] = 0u;
     __syncthreads();
     const int32_t* srcq = bt.hclq + ((size_t)b * kHeurRoots + win) * n;
@@ -337,52 +405,118 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
       if (v < n && deg[v] >= L - 1) m |= 1u << k;
     }
     A[x] = m;
-    An[x] = m;
   }
   __syncthreads();
-  for (int round = 0; round < 256; ++round) {
-    if (tid == 0) s_changed = 0;
-    __syncthreads();
-    for (int x = wid; x < W; x += nw) {
-      uint32_t m = A[x];  // warp-uniform
-      while (m) {
-        int u[4], bits[4], d[4], kc = 0;
-        while (m && kc < 4) {
-          bits[kc] = __ffs(m) - 1;
-          m &= m - 1;
-          u[kc] = x * 32 + bits[kc];
-          ++kc;
-        }
-        for (int q = kc; q < 4; ++q) u[q] = u[0];
-        inset_degree4(bt, b, u, kc, A, W, lane, d);
-        if (lane == 0) {
-          uint32_t clr = 0u;
-          for (int q = 0; q < kc; ++q)
-            if (d[q] < L - 1) clr |= 1u << bits[q];
-          if (clr) {
-            atomicAnd(&An[x], ~clr);
-            s_changed = 1;
-          }
-        }
-      }
+  peel_to_core(bt, b, A, An, W, L - 1, &s_changed);
+  int alive = block_popcount(A, W, &s_cnt);
+
+  // ---- second-chance heuristic.  If far more than the incumbent survives its own core bound, the root-based
+  // greedy probably missed the dense part (e.g. a clique of ~1 % of the vertices planted in a 15 %-dense random
+  // graph: no top-degree vertex belongs to it).  Global peeling: repeatedly drop every vertex whose degree inside
+  // the surviving set is below the set's mean until the set is a clique.  A larger clique replaces the incumbent
+  // and the core bound is re-applied; the exact phase then starts from a strong lower bound.
+  if (alive > 4 * L + 64) {
+    int32_t* dg = bt.hclq + (size_t)b * kHeurRoots * n;  // the heuristic candidates are no longer needed
+    for (int x = tid; x < W; x += blockDim.x) {
+      S[x] = A[x];
+      An[x] = A[x];
     }
     __syncthreads();
-    const int ch = s_changed;
-    for (int x = tid; x < W; x += blockDim.x) A[x] = An[x];
-    __syncthreads();
-    if (!ch) break;
+    int cnt = alive;
+    bool is_clique = false;
+    for (int round = 0; round < 4096 && cnt > L; ++round) {
+      peel_round(bt, b, S, An, W, -1, dg, &s_changed);  // degrees only (threshold -1 removes nothing)
+      unsigned long long sum = 0ull, mn = ~0ull;
+      for (int x = tid; x < W; x += blockDim.x) {
+        uint32_t m = S[x];
+        while (m) {
+          const int v = x * 32 + (__ffs(m) - 1);
+          m &= m - 1;
+          sum += (unsigned)dg[v];
+          mn = min(mn, (unsigned long long)(unsigned)dg[v]);
+        }
+      }
+      // block reductions of the degree sum and minimum
+      if (tid == 0) {
+        s_sum = 0ull;
+        s_min = 0xffffffffu;
+      }
+      __syncthreads();
+      sum = __reduce_add_sync(0xffffffffu, (unsigned)(sum & 0xffffffffu)) +
+            ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)(sum >> 32)) << 32);
+      const unsigned mnw = __reduce_min_sync(0xffffffffu, (unsigned)min(mn, 0xffffffffull));
+      if ((tid & 31) == 0) {
+        atomicAdd(&s_sum, sum);
+        atomicMin(&s_min, mnw);
+      }
+      __syncthreads();
+      const unsigned long long tot = s_sum;
+      const int dmin = (int)s_min;
+      if (dmin == cnt - 1) {
+        is_clique = true;
+        break;
+      }
+      // drop every vertex with degree * cnt < total (below the mean); all-equal degrees: drop the lowest vertex
+      int removed_any = 0;
+      for (int x = tid; x < W; x += blockDim.x) {
+        uint32_t m = S[x], keep = m;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          if ((unsigned long long)(unsigned)dg[x * 32 + bit] * (unsigned long long)cnt < tot) keep &= ~(1u << bit);
+        }
+        if (keep != S[x]) removed_any = 1;
+        An[x] = keep;
+      }
+      removed_any = __syncthreads_or(removed_any);
+      if (!removed_any) {
+        if (tid == 0) {
+          for (int x = 0; x < W; ++x)
+            if (An[x]) {
+              An[x] &= An[x] - 1;  // clear the lowest set bit
+              break;
+            }
+        }
+        __syncthreads();
+      }
+      for (int x = tid; x < W; x += blockDim.x) S[x] = An[x];
+      __syncthreads();
+      cnt = block_popcount(S, W, &s_cnt);
+    }
+    if (is_clique && cnt > L) {
+      // new incumbent: S
+      L = cnt;
+      if (tid == 0) {
+        int32_t* dst = bt.clq + (size_t)b * n;
+        int k = 0;
+        for (int x = 0; x < W; ++x) {
+          uint32_t m = S[x];
+          while (m) {
+            dst[k++] = x * 32 + (__ffs(m) - 1);
+            m &= m - 1;
+          }
+        }
+        bt.L[b] = L;
+      }
+      for (int x = tid; x < W; x += blockDim.x) bb[x] = S[x];
+      __syncthreads();
+      // re-apply the (L-1)-core bound with the stronger L (A is still a superset of the new core)
+      for (int x = tid; x < W; x += blockDim.x) {
+        uint32_t m = A[x], keep = m;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          if (deg[x * 32 + bit] < L - 1) keep &= ~(1u << bit);
+        }
+        A[x] = keep;
+      }
+      __syncthreads();
+      peel_to_core(bt, b, A, An, W, L - 1, &s_changed);
+      alive = block_popcount(A, W, &s_cnt);
+    }
   }
-  if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  int c = 0;
-  for (int x = tid; x < W; x += blockDim.x) {
-    alive_g[x] = A[x];
-    c += __popc(A[x]);
-  }
-  c = __reduce_add_sync(0xffffffffu, c);
-  if (lane == 0 && c) atomicAdd(&s_cnt, c);
-  __syncthreads();
-  if (tid == 0) bt.alive_cnt[b] = s_cnt;
+  for (int x = tid; x < W; x += blockDim.x) alive_g[x] = A[x];
+  if (tid == 0) bt.alive_cnt[b] = alive;
 }
 
 // =================================================================================================
