@@ -62,3 +62,11 @@ def test_no_cpu_fallback(tp):
     s = tp.RobustRegistrationSolver(tp.RobustRegistrationSolver.Params())
     with pytest.raises(RuntimeError):
         s.solve(np.zeros((3, 10)), np.ones((3, 10)))
+
+
+def test_mex_shim_compiles_against_stub():
+    """matlab/teaser_mex.cc (MATLAB absent here): syntax/type check against a stub of the MEX API."""
+    mex = os.path.join(HOST, "matlab")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-fsyntax-only", "-DTZR_MEX_SYNTAX_CHECK", "-I", mex,
+                           "-I", os.path.join(ROOT, "include"), os.path.join(mex, "teaser_mex.cc")])

@@ -671,3 +671,26 @@ def test_clique_time_limit_is_honoured(ctx):
     gc, proven = ctx.max_clique(bits, n, mode=0, time_limit=1e-6)
     assert not proven and len(gc) >= 2
     assert all(A[a, b] for a in gc for b in gc if a != b)
+
+
+def test_batch_c4_shape(ctx):
+    """BASELINE config C4 shape (N=2000, 90 % outliers) as a batch: every problem recovers its planted inlier set
+    (or a superset containing it) and the ground-truth pose; a sample is compared with the oracle."""
+    B = 96
+    prs = [synth.config_problem("C4", b) for b in range(B)]
+    src = np.ascontiguousarray(np.stack([q["src"] for q in prs]))
+    dst = np.ascontiguousarray(np.stack([q["dst"] for q in prs]))
+    p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
+    sols, cl = ctx.solve_batch_array(src, dst, p)
+    for b in range(B):
+        m = sols[b]["clique_size"]
+        assert sols[b]["valid"] and sols[b]["clique_proven_optimal"] == 1
+        assert set(prs[b]["inliers"].tolist()) <= set(cl[b, :m].tolist())
+        R = capi.rotation_from_solution_record(sols[b])
+        assert synth.angular_error(prs[b]["R"], R) < 0.02 and np.linalg.norm(prs[b]["t"] - sols[b]["translation"]) < 0.02
+    for b in (0, 17, 95):
+        o = orc.solve(prs[b]["src"], prs[b]["dst"], orc.default_params(**fixed_params(prs[b]["noise_bound"])))
+        m = sols[b]["clique_size"]
+        assert np.array_equal(cl[b, :m], o["clique"])
+        assert synth.angular_error(o["R"], capi.rotation_from_solution_record(sols[b])) <= ROT_TOL
+        assert np.linalg.norm(o["t"] - sols[b]["translation"]) <= TRANS_TOL
