@@ -81,7 +81,7 @@ _SYMBOLS = [
     "tzr_ctx_destroy", "tzr_ctx_set_stream", "tzr_ctx_synchronize", "tzr_ctx_kernel_launches", "tzr_words_per_row",
     "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_tls_translation", "tzr_scalar_tls",
     "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
-    "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks",
+    "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks", "tzr_ctx_debug_counters",
 ]
 
 
@@ -133,6 +133,7 @@ def lib():
     L.tzr_ctx_filter_mismatches.restype = C.c_int64
     L.tzr_ctx_filter_rechecks.argtypes = [vp]
     L.tzr_ctx_filter_rechecks.restype = C.c_int64
+    L.tzr_ctx_debug_counters.argtypes = [vp, i64p]
     for s in _SYMBOLS:
         getattr(L, s)  # raises AttributeError if the header and the library disagree
     _lib = L
@@ -193,6 +194,13 @@ class Context:
 
     def filter_rechecks(self) -> int:
         return int(lib().tzr_ctx_filter_rechecks(self._h))
+
+    def debug_counters(self):
+        out = np.zeros(16, dtype=np.int64)
+        self._ck(lib().tzr_ctx_debug_counters(self._h, _p(out, C.c_int64)))
+        return dict(filter_mismatches=int(out[0]), filter_rechecks=int(out[1]), clique_nodes=int(out[2]),
+                    reduce_rounds=int(out[3]), reduce_vertices=int(out[4]), colourings=int(out[5]),
+                    coloured_vertices=int(out[6]))
 
     def kernel_launches(self) -> int:
         return int(lib().tzr_ctx_kernel_launches(self._h))

@@ -165,7 +165,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   ENS(rmask, (size_t)B * bt.rot_cap);
   ENS(tmask, Bn);
   ENS(sol, (size_t)B * sizeof(tzr_solution));
-  ENS(dbg, 2 * sizeof(unsigned long long));
+  ENS(dbg, 16 * sizeof(unsigned long long));
 #undef ENS
   bt.src = (const double*)ctx->src.p;
   bt.dst = (const double*)ctx->dst.p;
@@ -327,7 +327,7 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev) 
   }
   cudaEventRecord(ev[0], st);
   init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(bt.sol, bt.B);
-  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
+  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 16 * sizeof(unsigned long long), st);
   ctx->launches += 1;
   if (bt.scale_mode) {  // before prep: the FP32 filter copies are pre-scaled by the estimate
     bt.beta = 2.0 * p.noise_bound * std::sqrt(p.cbar2);
@@ -521,6 +521,13 @@ int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx) {
   return (int64_t)v;
 }
 
+int tzr_ctx_debug_counters(tzr_ctx* ctx, int64_t* out16) {
+  if (!ctx || !ctx->dbg.p || !out16) return TZR_ERR_INVALID_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  if (cudaMemcpy(out16, ctx->dbg.p, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return TZR_ERR_CUDA;
+  return TZR_OK;
+}
+
 int64_t tzr_ctx_filter_rechecks(tzr_ctx* ctx) {
   if (!ctx || !ctx->dbg.p) return -1;
   unsigned long long v = 0;
@@ -543,7 +550,7 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, d
   bt.beta = beta;
   CK(cudaMemcpyAsync((void*)bt.src, src, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync((void*)bt.dst, dst, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 2 * sizeof(unsigned long long), st);
+  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 16 * sizeof(unsigned long long), st);
   launch_prep(bt, st);
   launch_graph(bt, st);
   launch_degree(bt, st);

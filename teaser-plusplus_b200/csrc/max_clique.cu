@@ -45,13 +45,13 @@ __device__ __forceinline__ const uint32_t* adj_row32(const Batch& bt, int b, int
 // vertices are independent, so one warp keeps 4x the memory-level parallelism of a one-vertex-at-a-time loop
 // (these kernels are latency-bound on the L2/HBM-resident bitset, not bandwidth-bound).
 __device__ __forceinline__ void inset_degree4(const Batch& bt, int b, const int u[4], int cnt, const uint32_t* S,
-                                              int W, int lane, int d[4]) {
+                                              int W, int lane, int d[4], int xlo = 0) {
   const uint32_t* r0 = adj_row32(bt, b, u[0]);
   const uint32_t* r1 = adj_row32(bt, b, cnt > 1 ? u[1] : u[0]);
   const uint32_t* r2 = adj_row32(bt, b, cnt > 2 ? u[2] : u[0]);
   const uint32_t* r3 = adj_row32(bt, b, cnt > 3 ? u[3] : u[0]);
   int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-  for (int y = lane; y < W; y += 32) {
+  for (int y = xlo + lane; y < W; y += 32) {  // words below xlo are known to be empty in S
     const uint32_t sw = S[y];
     const uint32_t a0 = r0[y], a1 = r1[y], a2 = r2[y], a3 = r3[y];
     d0 += __popc(a0 & sw);
@@ -456,14 +456,18 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
         is_clique = true;
         break;
       }
-      // drop every vertex with degree * cnt < total (below the mean); all-equal degrees: drop the lowest vertex
+      // far from a clique (mean degree < 3/4 of cnt-1): drop every vertex below the mean degree; close to one:
+      // drop only the minimum-degree vertices (the mean rule would start cutting clique members).
+      const bool coarse = tot * 4ull < 3ull * (unsigned long long)cnt * (unsigned long long)(cnt - 1);
       int removed_any = 0;
       for (int x = tid; x < W; x += blockDim.x) {
         uint32_t m = S[x], keep = m;
         while (m) {
           const int bit = __ffs(m) - 1;
           m &= m - 1;
-          if ((unsigned long long)(unsigned)dg[x * 32 + bit] * (unsigned long long)cnt < tot) keep &= ~(1u << bit);
+          const unsigned dv = (unsigned)dg[x * 32 + bit];
+          const bool drop = coarse ? ((unsigned long long)dv * (unsigned long long)cnt < tot) : ((int)dv == dmin);
+          if (drop) keep &= ~(1u << bit);
         }
         if (keep != S[x]) removed_any = 1;
         An[x] = keep;
@@ -481,6 +485,41 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
       }
       for (int x = tid; x < W; x += blockDim.x) S[x] = An[x];
       __syncthreads();
+      cnt = block_popcount(S, W, &s_cnt);
+    }
+    if (is_clique) {
+      // greedy extension: every alive vertex adjacent to ALL of S may still join (the peeling above is lossy);
+      // CN = A ∩ (∩_{s∈S} N(s)); then repeatedly take the lowest vertex of CN and intersect with its row.
+      for (int x = tid; x < W; x += blockDim.x) An[x] = A[x] & ~S[x];
+      __syncthreads();
+      for (int x0 = 0; x0 < W; ++x0) {
+        uint32_t m = S[x0];  // uniform
+        while (m) {
+          const int sv = x0 * 32 + (__ffs(m) - 1);
+          m &= m - 1;
+          const uint32_t* rs = adj_row32(bt, b, sv);
+          for (int x = tid; x < W; x += blockDim.x) An[x] &= rs[x];
+        }
+      }
+      __syncthreads();
+      __shared__ int s_pick;
+      for (int it = 0; it < n; ++it) {
+        if (tid == 0) {
+          s_pick = -1;
+          for (int x = 0; x < W; ++x)
+            if (An[x]) {
+              s_pick = x * 32 + (__ffs(An[x]) - 1);
+              break;
+            }
+        }
+        __syncthreads();
+        const int v = s_pick;
+        if (v < 0) break;
+        const uint32_t* rv = adj_row32(bt, b, v);
+        for (int x = tid; x < W; x += blockDim.x) An[x] &= rv[x];
+        if (tid == 0) S[v >> 5] |= 1u << (v & 31);
+        __syncthreads();
+      }
       cnt = block_popcount(S, W, &s_cnt);
     }
     if (is_clique && cnt > L) {
@@ -661,6 +700,7 @@ __device__ __forceinline__ int warp_first_bit(const uint32_t* bits, int W, int l
 }
 
 struct WarpCtx {
+  unsigned long long* cnt;  // debug counters (nullptr unless debug flag 4): see tzr_ctx_debug_counters
   const Batch* bt;
   int b, n, W, lane;
   uint32_t *Pc, *Q, *R, *Bs;     // shared memory (this warp)
@@ -668,6 +708,7 @@ struct WarpCtx {
   int32_t* cv;                   // global: current clique
   int32_t* centry;               // global: clique size at entry of level d
   volatile int32_t* Lp;
+  int xlo;                       // word index of the current root: every candidate set is empty below it
 };
 
 // Reduce the node in Pc.  Returns: 0 pruned, 1 leaf (Pc empty, csz >= incumbent size), 2 continue.
@@ -675,6 +716,10 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
   const int W = c.W, lane = c.lane;
   for (int round = 0; round < 8; ++round) {
     const int cnt = warp_popc(c.Pc, W, lane);
+    if (c.cnt && lane == 0) {
+      atomicAdd(c.cnt + 3, 1ull);
+      atomicAdd(c.cnt + 4, (unsigned long long)cnt);
+    }
     const int Lc = *c.Lp;
     if (csz + cnt < Lc) return 0;  // cannot even tie the incumbent (ties are enumerated: canonical result)
     if (cnt == 0) return 1;
@@ -684,8 +729,8 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     bool changed = false;
     int added = 0;
     {
-      int x = 0;
-      uint32_t m = c.Pc[0];  // warp-uniform (shared memory broadcast)
+      int x = c.xlo;
+      uint32_t m = c.Pc[x];  // warp-uniform (shared memory broadcast)
       while (true) {
         int u[4], d[4], kc = 0;
         while (kc < 4) {
@@ -697,7 +742,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
         }
         if (kc == 0) break;
         for (int q = kc; q < 4; ++q) u[q] = u[0];
-        inset_degree4(*c.bt, c.b, u, kc, c.Pc, W, lane, d);
+        inset_degree4(*c.bt, c.b, u, kc, c.Pc, W, lane, d, c.xlo);
         for (int q = 0; q < kc; ++q) {
           if (d[q] == cnt - 1) {  // universal: belongs to every maximal clique of this node
             if (lane == 0) {
@@ -741,8 +786,13 @@ __device__ int node_colour(WarpCtx& c, int csz) {
     c.Bs[x] = 0u;
   }
   __syncwarp();
+  const int warp_popc_lane0_hint = c.cnt ? warp_popc(c.Pc, W, lane) : 0;
   int nB = 0;
   int qstart = 0;
+  if (c.cnt && lane == 0) {
+    atomicAdd(c.cnt + 5, 1ull);
+    atomicAdd(c.cnt + 6, (unsigned long long)warp_popc_lane0_hint);
+  }
   for (int k = 1;; ++k) {
     // anything left uncoloured?
     int xq;
@@ -835,6 +885,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* wbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * 4 * W;
   WarpCtx c;
+  c.cnt = (bt.flags_dbg & 4u) ? bt.mismatches : nullptr;
   c.bt = &bt;
   c.b = b;
   c.n = n;
@@ -883,6 +934,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
       __syncwarp();
     }
     if (lane == 0) c.cv[0] = v;
+    c.xlo = v >> 5;
     __syncwarp();
     int csz = 1;
     int depth = 0;  // number of saved levels
@@ -895,6 +947,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
           depth = 0;
           break;
         }
+        if (c.cnt && lane == 0) atomicAdd(c.cnt + 2, 1ull);
         const int r = node_reduce(c, csz);
         if (r == 1) {
           if (csz >= *c.Lp) record_clique(c, csz);
