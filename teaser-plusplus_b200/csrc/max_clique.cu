@@ -554,7 +554,11 @@ __global__ void __launch_bounds__(kPeelThreads) clique_peel_kernel(Batch bt, int
       alive = block_popcount(A, W, &s_cnt);
     }
   }
-  for (int x = tid; x < W; x += blockDim.x) alive_g[x] = A[x];
+  // If exactly L vertices survive the (L-1)-core bound they ARE the incumbent clique (its members always survive):
+  // no other clique of size >= L can exist, the maximum clique is unique and proven — the exact phase is skipped.
+  // This is the GPU counterpart of the reference's `lb == ub` early return (graph.cc:100-102).
+  if (alive == L) alive = 0;
+  for (int x = tid; x < W; x += blockDim.x) alive_g[x] = alive ? A[x] : 0u;
   if (tid == 0) bt.alive_cnt[b] = alive;
 }
 

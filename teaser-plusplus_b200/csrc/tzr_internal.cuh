@@ -20,7 +20,8 @@ __host__ __device__ inline int words64(int n) { return (n + 63) / 64; }
 
 constexpr int kTile = 128;          // graph tile edge (pairs per tile = 128*128)
 constexpr int kGraphThreads = 128;  // 4 warps, each owns a 32x128 sub-tile (4 pairs per lane per step)
-constexpr int kHeurRoots = 8;       // heuristic start vertices per problem (top degrees)
+constexpr int kHeurRoots = 4;       // heuristic start vertices per problem (top degrees); a global-peeling
+                                    // second chance in the peel kernel covers the cases they all miss
 constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memory clique kernels
 
 // Per-problem constants of the FP32 filter (see graph_build.cu).
