@@ -1,0 +1,12 @@
+#!/bin/sh
+# Re-creates tests/golden/ from the reference tree (run in the build container, where /root/reference exists).
+set -e
+REF=${1:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+for i in 1 2 3 4 5 6; do cp -r "$REF/test/benchmark/data/benchmark_$i" "$HERE/"; done
+mkdir -p "$HERE/registration_test"
+for f in objectIn.csv sceneIn.csv rotation_only_src.csv translation_test_v1_inliers.csv translation_test_v2_inliers.csv; do
+  cp "$REF/test/teaser/data/registration_test/$f" "$HERE/registration_test/"
+done
+cp "$REF/examples/example_data/bun_zipper_res3.ply" "$HERE/"
+chmod -R u+w "$HERE"
