@@ -38,6 +38,8 @@ struct tzr_ctx {
   int graph_ev_used = 0;
   std::vector<cudaEvent_t> stage_ev;  // 5 per chunk of the last pipelined call (stage timing is summed over chunks)
   int stage_chunks = 0;
+  cudaStream_t stream2 = nullptr;      // second compute stream: chunk tails overlap the next chunk's graph kernel
+  cudaEvent_t join_ev = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D of chunk k+1 overlaps the kernels of chunk k (host-pointer batches)
   std::vector<cudaEvent_t> chunk_ev;
 };
@@ -283,8 +285,7 @@ int l2_chunk(const tzr_ctx* ctx, int B, int n, const tzr_params& p) {
 }
 
 // The fused device pipeline for one uniform batch.  src/dst must already be set in bt.
-int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev) {
-  cudaStream_t st = ctx->stream;
+int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, cudaStream_t st) {
   if (p.rotation_estimation_algorithm < 0 || p.rotation_estimation_algorithm > 2 || p.rotation_tim_graph < 0 ||
       p.rotation_tim_graph > 1)
     return TZR_ERR_INVALID_ARG;
@@ -383,15 +384,27 @@ int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, int chunk, const c
     if (cudaEventCreate(&e) != cudaSuccess) return TZR_ERR_CUDA;
     ctx->stage_ev.push_back(e);
   }
+  // chunks alternate between two compute streams (their scratch is disjoint): the latency-bound tail of chunk k
+  // (peel / exact / rot+trans on a few dozen CTAs) overlaps the graph kernel of chunk k+1
+  const bool two = n_chunks > 1 && ctx->stream2 != nullptr;
+  if (two) {
+    if (cudaEventRecord(ctx->join_ev, ctx->stream) != cudaSuccess) return TZR_ERR_CUDA;
+    if (cudaStreamWaitEvent(ctx->stream2, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
+  }
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = c * chunk, Bc = std::min(chunk, bt.B - b0);
+    cudaStream_t st = (two && (c & 1)) ? ctx->stream2 : ctx->stream;
     if (ready) {
-      if (cudaStreamWaitEvent(ctx->stream, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
+      if (cudaStreamWaitEvent(st, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
     }
     Batch sb = (n_chunks > 1) ? sub_batch(bt, b0, Bc) : bt;
-    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * c);
+    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * c, st);
     if (rc) return rc;
     if (n_chunks == 1) bt = sb;  // keep fields filled in by run_pipeline (beta, scale_mode, ...)
+  }
+  if (two) {  // everything later on ctx->stream (D2H, the caller's work) is ordered after stream2 as well
+    if (cudaEventRecord(ctx->join_ev, ctx->stream2) != cudaSuccess) return TZR_ERR_CUDA;
+    if (cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
   }
   ctx->stage_chunks = n_chunks;
   ctx->last = bt;
@@ -462,6 +475,8 @@ int tzr_ctx_create(int device, tzr_ctx** out) {
   }
   for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
   *out = ctx;
   return TZR_OK;
 }
@@ -484,6 +499,8 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   for (cudaEvent_t e : ctx->stage_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->graph_ev) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return TZR_OK;
@@ -800,8 +817,16 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
   rc = run_chunked(ctx, bt, *params, chunk, n_chunks > 1 ? ctx->chunk_ev.data() : nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));
-  if (cliques) CK(cudaMemcpyAsync(h_clq, bt.sorted_clq, (size_t)B * n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (cliques) {  // only the used prefix of every clique row crosses PCIe (rows are n int32 wide, cliques ~5 % of n)
+    int max_m = 0;
+    for (int b = 0; b < B; ++b) max_m = std::max(max_m, std::min(n, std::max(0, h_sol[b].clique_size)));
+    if (max_m > 0) {
+      CK(cudaMemcpy2DAsync(h_clq, (size_t)n * sizeof(int32_t), bt.sorted_clq, (size_t)n * sizeof(int32_t),
+                           (size_t)max_m * sizeof(int32_t), B, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
   memcpy(solutions, h_sol, (size_t)B * sizeof(tzr_solution));
   for (int b = 0; b < B; ++b)
     if (h_sol[b].clique_proven_optimal == -2) {
