@@ -124,6 +124,13 @@ int tzr_gnc_tls_rotation(tzr_ctx* ctx, const double* src_3xM, const double* dst_
                          double gnc_factor, uint64_t max_iterations, double cost_threshold, double* R_colmajor9,
                          uint8_t* inlier_mask, double* cost_at_termination, int32_t* iterations);
 
+/* Same stage for any of the reference's rotation back-ends on caller-supplied TIMs: algorithm 0 GNC_TLS
+ * (registration.cc:764-866), 1 FGR (FastGlobalRegistrationSolver::solveForRotation, registration.cc:206-278),
+ * 2 QUATRO (QuatroSolver::solveForRotation, registration.cc:280-408; yaw only). */
+int tzr_rotation_solve(tzr_ctx* ctx, int algorithm, const double* src_3xM, const double* dst_3xM, int m,
+                       double noise_bound, double gnc_factor, uint64_t max_iterations, double cost_threshold,
+                       double* R_colmajor9, uint8_t* inlier_mask, double* cost_at_termination, int32_t* iterations);
+
 /* ---- stage 4: TLS translation ---------------------------------------------------------------
  * Replaces TLSTranslationSolver::solveForTranslation (registration.cc:445-471): per-axis
  * ScalarTLSEstimator::estimate on dst - src with range noise_bound*sqrt(cbar2). */

@@ -79,7 +79,7 @@ _lib = None
 _SYMBOLS = [
     "tzr_abi_version", "tzr_status_string", "tzr_last_error", "tzr_params_default", "tzr_ctx_create",
     "tzr_ctx_destroy", "tzr_ctx_set_stream", "tzr_ctx_synchronize", "tzr_ctx_kernel_launches", "tzr_words_per_row",
-    "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_tls_translation", "tzr_scalar_tls",
+    "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_rotation_solve", "tzr_tls_translation", "tzr_scalar_tls",
     "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
     "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks", "tzr_ctx_debug_counters",
 ]
@@ -120,6 +120,8 @@ def lib():
     L.tzr_max_clique.argtypes = [vp, u64p, C.c_int, C.c_int, C.c_double, C.c_double, i32p, i32p, i32p]
     L.tzr_gnc_tls_rotation.argtypes = [vp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_double, dp, u8p,
                                        dp, i32p]
+    L.tzr_rotation_solve.argtypes = [vp, C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_double, dp,
+                                     u8p, dp, i32p]
     L.tzr_tls_translation.argtypes = [vp, dp, dp, C.c_int, C.c_double, C.c_double, dp, u8p]
     L.tzr_scalar_tls.argtypes = [vp, dp, dp, C.c_int64, dp, u8p]
     L.tzr_solve.argtypes = [vp, C.POINTER(Params), dp, dp, C.c_int, C.POINTER(Solution), i32p, u8p, u8p]
@@ -238,15 +240,20 @@ class Context:
         return out[:m.value].copy(), bool(proven.value)
 
     def gnc_tls_rotation(self, src, dst, noise_bound, gnc_factor=1.4, max_iterations=100, cost_threshold=1e-6):
+        return self.rotation_solve(0, src, dst, noise_bound, gnc_factor, max_iterations, cost_threshold)
+
+    def rotation_solve(self, algorithm, src, dst, noise_bound, gnc_factor=1.4, max_iterations=100,
+                       cost_threshold=1e-6):
+        """algorithm: 0 GNC_TLS, 1 FGR, 2 QUATRO (ROTATION_ESTIMATION_ALGORITHM, registration.h:382-386)."""
         s, d = _pts(src), _pts(dst)
         m = s.shape[0]
         R = np.zeros(9)
         mask = np.zeros(m, dtype=np.uint8)
         cost = C.c_double()
         it = C.c_int32()
-        self._ck(lib().tzr_gnc_tls_rotation(self._h, _p(s, C.c_double), _p(d, C.c_double), m, noise_bound, gnc_factor,
-                                            int(max_iterations), cost_threshold, _p(R, C.c_double),
-                                            _p(mask, C.c_uint8), C.byref(cost), C.byref(it)))
+        self._ck(lib().tzr_rotation_solve(self._h, int(algorithm), _p(s, C.c_double), _p(d, C.c_double), m, noise_bound,
+                                          gnc_factor, int(max_iterations), cost_threshold, _p(R, C.c_double),
+                                          _p(mask, C.c_uint8), C.byref(cost), C.byref(it)))
         return dict(R=R.reshape(3, 3).T.copy(), inliers=mask.astype(bool), cost=cost.value, iterations=it.value)
 
     def tls_translation(self, src, dst, noise_bound, cbar2=1.0):

@@ -25,7 +25,7 @@ struct tzr_ctx {
   uint32_t flags = 0;
   int num_sms = 148;
   // device buffers (grow-only)
-  DevBuf src, dst, sf, df, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
+  DevBuf src, dst, sf, df, pk, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
       centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx;
   // pinned host staging
   void* h_pin = nullptr;
@@ -118,6 +118,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   }
   ENS(sf, Bn * sizeof(float4));
   ENS(df, Bn * sizeof(float4));
+  ENS(pk, (size_t)B * 6 * npad128(n) * sizeof(float));
   ENS(gc, (size_t)B * sizeof(GraphConsts));
   ENS(adj, Bn * pitch64(n) * sizeof(uint64_t));
   ENS(deg, Bn * sizeof(int32_t));
@@ -173,6 +174,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   bt.dst = (const double*)ctx->dst.p;
   bt.sf = (float4*)ctx->sf.p;
   bt.df = (float4*)ctx->df.p;
+  bt.pk = (float*)ctx->pk.p;
   bt.gc = (GraphConsts*)ctx->gc.p;
   bt.adj = (uint64_t*)ctx->adj.p;
   bt.deg = (int32_t*)ctx->deg.p;
@@ -240,6 +242,7 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
   s.dst = bt.dst + o * n * 3;
   s.sf = bt.sf + o * n;
   s.df = bt.df + o * n;
+  s.pk = bt.pk + o * 6 * (size_t)npad128(bt.n);
   s.gc = bt.gc + o;
   s.adj = bt.adj + o * n * pitch64(bt.n);
   s.deg = bt.deg + o * n;
@@ -485,7 +488,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   if (!ctx) return TZR_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
+  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->pk, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->tstart, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
@@ -629,7 +632,14 @@ int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, doub
 int tzr_gnc_tls_rotation(tzr_ctx* ctx, const double* src, const double* dst, int m, double noise_bound,
                          double gnc_factor, uint64_t max_iterations, double cost_threshold, double* R,
                          uint8_t* inlier_mask, double* cost, int32_t* iterations) {
-  if (!ctx || !src || !dst || !R || m <= 0) return TZR_ERR_INVALID_ARG;
+  return tzr_rotation_solve(ctx, 0, src, dst, m, noise_bound, gnc_factor, max_iterations, cost_threshold, R,
+                            inlier_mask, cost, iterations);
+}
+
+int tzr_rotation_solve(tzr_ctx* ctx, int algorithm, const double* src, const double* dst, int m, double noise_bound,
+                       double gnc_factor, uint64_t max_iterations, double cost_threshold, double* R,
+                       uint8_t* inlier_mask, double* cost, int32_t* iterations) {
+  if (!ctx || !src || !dst || !R || m <= 0 || algorithm < 0 || algorithm > 2) return TZR_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   const size_t pts = (size_t)m * 3 * sizeof(double);
@@ -645,7 +655,7 @@ int tzr_gnc_tls_rotation(tzr_ctx* ctx, const double* src, const double* dst, int
   uint8_t* d_mask = (uint8_t*)(d_out + 12);
   CK(cudaMemcpyAsync(d_src, src, pts, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_dst, dst, pts, cudaMemcpyHostToDevice, st));
-  launch_gnc_only(d_src, d_dst, m, noise_bound, gnc_factor, max_iterations, cost_threshold, d_w, d_r, d_out, d_mask,
+  launch_gnc_only(algorithm, d_src, d_dst, m, noise_bound, gnc_factor, max_iterations, cost_threshold, d_w, d_r, d_out, d_mask,
                   d_out + 9, d_it, st);
   ctx->launches += 1;
   rc = check_launch(ctx, "gnc");

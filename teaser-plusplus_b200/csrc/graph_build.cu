@@ -164,6 +164,23 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     sf[i] = a;
     df[i] = c;
   }
+  // pair-interleaved copy for the packed kernel: (point o, point o+32) of every 64-column half block adjacent
+  const int npad = npad128(n);
+  float* pk = bt.pk + (size_t)b * 6 * npad;
+  for (int j = threadIdx.x; j < npad; j += blockDim.x) {
+    const int o = j & 127, pos = (j & ~127) + (o >> 6) * 64 + (o & 31) * 2 + ((o >> 5) & 1);
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (j < n) {
+      v[0] = (float)((src[3 * j + 0] - s_c[0]) * s_c[6]);
+      v[1] = (float)((src[3 * j + 1] - s_c[1]) * s_c[6]);
+      v[2] = (float)((src[3 * j + 2] - s_c[2]) * s_c[6]);
+      v[3] = (float)(dst[3 * j + 0] - s_c[3]);
+      v[4] = (float)(dst[3 * j + 1] - s_c[4]);
+      v[5] = (float)(dst[3 * j + 2] - s_c[5]);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) pk[(size_t)q * npad + pos] = v[q];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -522,6 +539,210 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// graph strip kernel, packed-FP32 variant (default): identical decomposition and outputs as graph_strip_kernel,
+// but the twelve FP32 operations per pair run as sm_100 packed instructions (FADD2 / FMUL2 / FFMA2 via
+// __fadd2_rn / __fmul2_rn / __ffma2_rn: two pairs per instruction), because the scalar kernel is ISSUE-bound
+// (ncu: 75 % issue-active, FMA pipe 43 %): packing halves the FP32 issue slots at unchanged pipe work.  Every
+// component is the same IEEE operation as in the scalar kernel, so the classification (and delta) is unchanged.
+// The row point is stored negated and duplicated in shared memory ((-x,-x), ...) so that js - is is one FADD2.
+// ------------------------------------------------------------------------------------------------
+// packed FP32x2 values live in 64-bit registers end to end (PTX *.f32x2), so no re-packing moves are needed
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+struct __align__(16) IPointNeg2 {
+  float4 a;  // (-sx,-sx,-sy,-sy)
+  float4 b;  // (-sz,-sz,-dx,-dx)
+  float4 c;  // (-dy,-dy,-dz,-dz)
+};
+
+template <bool kVerify, int kMinBlocks>
+__global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel(Batch bt) {
+  const int b = blockIdx.y;
+  const int n = bt.n;
+  const int nt = (n + kTile - 1) / kTile;
+  int I = 0, p = blockIdx.x;
+  while (true) {
+    const int ng = (nt - I + kStripBlocks - 1) / kStripBlocks;
+    if (p < ng) break;
+    p -= ng;
+    ++I;
+  }
+  const int J0 = I + p * kStripBlocks;
+  const int J1 = min(nt, J0 + kStripBlocks);
+
+  __shared__ IPointNeg2 s_ip[kTile];
+  __shared__ __align__(16) uint32_t s_rw[kTile][4];
+
+  const GraphConsts* gcp = bt.gc + b;
+  const float b1 = gcp->b1, b2 = gcp->b2;
+  const double beta = gcp->beta;
+  const bool scale_mode = bt.scale_mode != 0;
+  const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
+
+  const float4* sf = bt.sf + (size_t)b * n;
+  const float4* df = bt.df + (size_t)b * n;
+  const double* src = bt.src + (size_t)b * n * 3;
+  const double* dst = bt.dst + (size_t)b * n * 3;
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int ibase = I * kTile + 32 * w;
+  const int nrows = min(32, n - ibase);
+  if (nrows <= 0) return;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int i = ibase + lane;
+    const float4 s = (i < n) ? sf[i] : z4, d = (i < n) ? df[i] : z4;
+    IPointNeg2 ip;
+    ip.a = make_float4(-s.x, -s.x, -s.y, -s.y);
+    ip.b = make_float4(-s.z, -s.z, -d.x, -d.x);
+    ip.c = make_float4(-d.y, -d.y, -d.z, -d.z);
+    s_ip[tid] = ip;
+  }
+  __syncwarp();
+  uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * pitch32(n);
+  const int P32 = pitch32(n);
+  const uint32_t rmask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
+
+  const int npadh = npad128(n) / 2;  // 64-bit elements per packed array
+  const f32x2* pkp = reinterpret_cast<const f32x2*>(bt.pk + (size_t)b * 6 * npad128(n));
+  for (int J = J0; J < J1; ++J) {
+    const int jb = J * kTile + lane;
+    // column points, two pairs per 64-bit register: X[k] = (x of point jb+64k, x of point jb+64k+32), loaded as
+    // 8-byte words from the pair-interleaved arrays written by prep_kernel (zero-padded past n)
+    f32x2 SX[2], SY[2], SZ[2], DX[2], DY[2], DZ[2];
+    bool vj[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      vj[2 * k] = jb + 64 * k < n;
+      vj[2 * k + 1] = jb + 64 * k + 32 < n;
+      const size_t e = (size_t)J * 64 + k * 32 + lane;
+      SX[k] = pkp[0 * (size_t)npadh + e]; SY[k] = pkp[1 * (size_t)npadh + e]; SZ[k] = pkp[2 * (size_t)npadh + e];
+      DX[k] = pkp[3 * (size_t)npadh + e]; DY[k] = pkp[4 * (size_t)npadh + e]; DZ[k] = pkp[5 * (size_t)npadh + e];
+    }
+    if (nrows < 32) *reinterpret_cast<uint4*>(&s_rw[tid][0]) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    // pair index c (word c of the row) = point jb + 32*c = packed slot (k = c>>1, component c&1)
+    auto classify4 = [&](int ii, bool sure[4], bool dec[4]) {
+      // three 16-byte broadcast loads: six (-v,-v) pairs, each already a 64-bit register pair
+      const ulonglong2* ipp = reinterpret_cast<const ulonglong2*>(&s_ip[32 * w + ii]);
+      const ulonglong2 qa = ipp[0], qb = ipp[1], qc = ipp[2];
+      const f32x2 nsx = qa.x, nsy = qa.y, nsz = qb.x, ndx = qb.y, ndy = qc.x, ndz = qc.y;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const f32x2 ax = add2(SX[k], nsx), ay = add2(SY[k], nsy), az = add2(SZ[k], nsz);
+        const f32x2 bx = add2(DX[k], ndx), by = add2(DY[k], ndy), bz = add2(DZ[k], ndz);
+        const f32x2 a = fma2(az, az, fma2(ay, ay, mul2(ax, ax)));
+        const f32x2 bb = fma2(bz, bz, fma2(by, by, mul2(bx, bx)));
+        float a0, a1, c0, c1;
+        upk2(a, a0, a1);
+        upk2(bb, c0, c1);
+        const float x0 = fabsf(sqrt_approx(a0) - sqrt_approx(c0));
+        const float x1 = fabsf(sqrt_approx(a1) - sqrt_approx(c1));
+        sure[2 * k] = x0 <= b1;
+        dec[2 * k] = sure[2 * k] || (x0 > b2);
+        sure[2 * k + 1] = x1 <= b1;
+        dec[2 * k + 1] = sure[2 * k + 1] || (x1 > b2);
+      }
+    };
+    uint32_t ambmask = 0u;
+    uint32_t bit = 1u;
+#pragma unroll 2
+    for (int ii = 0; ii < nrows; ++ii, bit <<= 1) {
+      bool sure[4], dec[4];
+      classify4(ii, sure, dec);
+      // NOTE word order: word c covers columns 32c..32c+31 = points jb + 32c; packed slot k holds points
+      // jb + 64k (component x) and jb + 64k + 32 (component y), i.e. words 2k and 2k+1.
+      uint32_t m[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) m[c] = __ballot_sync(0xffffffffu, sure[c]);
+      *reinterpret_cast<uint4*>(&s_rw[32 * w + ii][0]) = make_uint4(m[0], m[1], m[2], m[3]);
+      if (!__all_sync(0xffffffffu, dec[0] && dec[1] && dec[2] && dec[3])) ambmask |= bit;
+    }
+    __syncwarp();
+    while (ambmask) {
+      const int ii = __ffs(ambmask) - 1;
+      ambmask &= ambmask - 1;
+      const int i = ibase + ii;
+      bool sure[4], dec[4];
+      classify4(ii, sure, dec);
+      int nre = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = jb + 32 * c;
+        bool ex = false;
+        if (!dec[c] && vj[c] && j != i) {
+          ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
+          ++nre;
+        }
+        const uint32_t mex = __ballot_sync(0xffffffffu, ex);
+        if (lane == 0 && mex) s_rw[32 * w + ii][c] |= mex;
+      }
+      if (bt.rechecks) {
+        nre = __reduce_add_sync(0xffffffffu, nre);
+        if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
+      }
+    }
+    if (kVerify) {
+      for (int ii = 0; ii < nrows; ++ii) {
+        const int i = ibase + ii;
+        bool sure[4], dec[4];
+        classify4(ii, sure, dec);
+        int bad = 0;
+        for (int c = 0; c < 4; ++c) {
+          const int j = jb + 32 * c;
+          if (dec[c] && vj[c] && j != i)
+            bad += ((scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta)) !=
+                    sure[c]);
+        }
+        if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
+      }
+    }
+    __syncwarp();
+    const uint4 rw = *reinterpret_cast<const uint4*>(&s_rw[tid][0]);
+    uint32_t roww[4] = {rw.x, rw.y, rw.z, rw.w}, colw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t cm = __ballot_sync(0xffffffffu, vj[c]);
+      roww[c] &= cm;
+      if (I == J && c == w) roww[c] &= ~(1u << lane);
+      colw[c] = warp_transpose32(roww[c], lane) & rmask;
+    }
+    if (lane < nrows)
+      *reinterpret_cast<uint4*>(adj32 + (size_t)(ibase + lane) * P32 + 4 * J) =
+          make_uint4(roww[0], roww[1], roww[2], roww[3]);
+    if (I != J) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (vj[c]) adj32[(size_t)(jb + 32 * c) * P32 + 4 * I + w] = colw[c];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // degree kernel: deg[v] = popcount(row v); n_edges2[b] = sum of degrees.  One warp per row.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) degree_kernel(Batch bt) {
@@ -561,13 +782,17 @@ void launch_graph(const Batch& bt, cudaStream_t st) {
   }
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
   if (bt.flags_dbg & 2u)
-    graph_strip_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    graph_strip2_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
     graph_strip_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 32u)  // occupancy A/B: 5 CTAs/SM (96 registers)
     graph_strip_kernel<false, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else  // default: 8 CTAs/SM (64 registers, 32 warps/SM) — measured 6 % faster than 5 CTAs/SM (issue-latency bound)
+  else if (bt.flags_dbg & 64u)  // scalar-FP32 strip kernel (A/B against the packed default)
     graph_strip_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else if (bt.flags_dbg & 128u)  // packed kernel at 6 CTAs/SM
+    graph_strip2_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else  // default: packed FP32x2 strip kernel, 8 CTAs/SM
+    graph_strip2_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
 }
 
 void launch_degree(const Batch& bt, cudaStream_t st) {

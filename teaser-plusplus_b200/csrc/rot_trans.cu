@@ -641,7 +641,7 @@ void launch_rot_trans(const Batch& bt, const tzr_params& p, int use_clique, cuda
 // =================================================================================================
 // stand-alone stage kernels (per-stage C-ABI entry points)
 // =================================================================================================
-__global__ void __launch_bounds__(kRTThreads) gnc_only_kernel(const double* src, const double* dst, int m,
+__global__ void __launch_bounds__(kRTThreads) gnc_only_kernel(int alg, const double* src, const double* dst, int m,
                                                                double noise_bound, double gnc_factor,
                                                                unsigned long long max_iter, double cost_thr,
                                                                double* wgt, double* res, double* out_R, uint8_t* mask,
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kRTThreads) gnc_only_kernel(const double* src,
   ts.a = src;
   ts.b = dst;
   ts.inv_scale = 1.0;
-  gnc_tls_block(ts, false, max_iter, cost_thr, gnc_factor, noise_bound, wgt, mask, g, s_buf, &s_R);
+  rotation_block(alg, ts, max_iter, cost_thr, gnc_factor, noise_bound, wgt, mask, g, s_buf, &s_R);
   if (threadIdx.x == 0) {
     for (int k = 0; k < 9; ++k) out_R[k] = g.R.a[k];
     *out_cost = g.cost;
@@ -665,11 +665,11 @@ __global__ void __launch_bounds__(kRTThreads) gnc_only_kernel(const double* src,
   }
 }
 
-void launch_gnc_only(const double* src, const double* dst, int m, double noise_bound, double gnc_factor,
+void launch_gnc_only(int alg, const double* src, const double* dst, int m, double noise_bound, double gnc_factor,
                      unsigned long long max_iter, double cost_thr, double* wgt, double* res, double* out_R,
                      uint8_t* mask, double* out_cost, int* out_iters, cudaStream_t st) {
-  gnc_only_kernel<<<1, kRTThreads, 0, st>>>(src, dst, m, noise_bound, gnc_factor, max_iter, cost_thr, wgt, res, out_R,
-                                            mask, out_cost, out_iters);
+  gnc_only_kernel<<<1, kRTThreads, 0, st>>>(alg, src, dst, m, noise_bound, gnc_factor, max_iter, cost_thr, wgt, res,
+                                            out_R, mask, out_cost, out_iters);
 }
 
 // translation: raw = dst - src per axis, TLS with constant range beta

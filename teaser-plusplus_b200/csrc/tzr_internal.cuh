@@ -17,6 +17,7 @@ namespace tzr {
 __host__ __device__ inline int pitch64(int n) { return 2 * ((n + 127) / 128); }
 __host__ __device__ inline int pitch32(int n) { return 2 * pitch64(n); }
 __host__ __device__ inline int words64(int n) { return (n + 63) / 64; }
+__host__ __device__ inline int npad128(int n) { return 128 * ((n + 127) / 128); }
 
 constexpr int kTile = 128;          // graph tile edge (pairs per tile = 128*128)
 constexpr int kGraphThreads = 128;  // 4 warps, each owns a 32x128 sub-tile (4 pairs per lane per step)
@@ -44,6 +45,8 @@ struct Batch {
   const double* dst;  // B*n*3
   float4* sf;     // B*n centred float copies (w unused)
   float4* df;
+  float* pk;      // B*6*npad128(n): the same centred floats, pair-interleaved per 128-column block for the packed
+                  // FP32x2 graph kernel (arrays sx,sy,sz,dx,dy,dz; element of point j at blk*128 + k*64 + lane*2 + half)
   GraphConsts* gc;        // B
   uint64_t* adj;          // B*n*pitch64(n)
   int32_t* deg;           // B*n
@@ -112,7 +115,7 @@ size_t clique_peel_smem(int n);
 size_t clique_exact_smem(int n);
 
 // stand-alone stage helpers used by the per-stage C-ABI entry points
-void launch_gnc_only(const double* src, const double* dst, int m, double noise_bound, double gnc_factor,
+void launch_gnc_only(int alg, const double* src, const double* dst, int m, double noise_bound, double gnc_factor,
                      unsigned long long max_iter, double cost_thr, double* wgt, double* res, double* out_R,
                      uint8_t* mask, double* out_cost, int* out_iters, cudaStream_t st);
 void launch_translation_only(const double* src, const double* dst, int m, double beta, double* skey, int32_t* sidx,

@@ -138,8 +138,7 @@ class GNCTLSRotationSolver : public GNCRotationSolver {
   void solveForRotation(const Mat3X& src, const Mat3X& dst, Eigen::Matrix3d* rotation, BoolRow* inliers) override;
 };
 
-// registration.h:290-352 — FGR and Quatro run on the device inside solve() (Params::rotation_estimation_algorithm);
-// the stand-alone strategy objects have no C-ABI entry point yet: calling them directly throws (no CPU fallback).
+// registration.h:290-352 — FGR and Quatro (forward to tzr_rotation_solve; inside solve() they run fused on the device)
 class FastGlobalRegistrationSolver : public GNCRotationSolver {
  public:
   FastGlobalRegistrationSolver() = delete;

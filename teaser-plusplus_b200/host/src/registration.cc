@@ -118,29 +118,33 @@ void TLSTranslationSolver::solveForTranslation(const Mat3X& src, const Mat3X& ds
   if (inliers) mask_from_bytes(mask, m, inliers);
 }
 
-void GNCTLSRotationSolver::solveForRotation(const Mat3X& src, const Mat3X& dst, Eigen::Matrix3d* rotation,
-                                            BoolRow* inliers) {
+namespace {
+void rotation_via_abi(int alg, const char* who, const GNCRotationSolver::Params& prm, const Mat3X& src, const Mat3X& dst,
+                      Eigen::Matrix3d* rotation, BoolRow* inliers, double* cost_out) {
   const size_t m = static_cast<size_t>(src.cols());
   std::vector<uint8_t> mask(m);
   double R[9], cost = 0;
   int32_t iters = 0;
   tzr_ctx* ctx = b200_context();
-  int rc = tzr_gnc_tls_rotation(ctx, src.data(), dst.data(), static_cast<int>(m), params_.noise_bound,
-                                params_.gnc_factor, params_.max_iterations, params_.cost_threshold, R, mask.data(),
-                                &cost, &iters);
-  if (rc != TZR_OK) fail("GNCTLSRotationSolver::solveForRotation", rc, ctx);
-  cost_ = cost;
+  int rc = tzr_rotation_solve(ctx, alg, src.data(), dst.data(), static_cast<int>(m), prm.noise_bound, prm.gnc_factor,
+                              prm.max_iterations, prm.cost_threshold, R, mask.data(), &cost, &iters);
+  if (rc != TZR_OK) fail(who, rc, ctx);
+  *cost_out = cost;
   if (rotation) std::memcpy(rotation->data(), R, sizeof(R));  // both column-major
   if (inliers) mask_from_bytes(mask, m, inliers);
 }
+}  // namespace
 
-// The stand-alone FGR / Quatro strategy objects are reached through solve() (whole path on the device); calling
-// them directly on caller-supplied TIMs has no C-ABI entry point yet and fails loudly (no CPU fallback).
-void FastGlobalRegistrationSolver::solveForRotation(const Mat3X&, const Mat3X&, Eigen::Matrix3d*, BoolRow*) {
-  throw std::runtime_error("teaser (B200): stand-alone FastGlobalRegistrationSolver::solveForRotation is not exposed; use solve()");
+void GNCTLSRotationSolver::solveForRotation(const Mat3X& src, const Mat3X& dst, Eigen::Matrix3d* rotation,
+                                            BoolRow* inliers) {
+  rotation_via_abi(0, "GNCTLSRotationSolver::solveForRotation", params_, src, dst, rotation, inliers, &cost_);
 }
-void QuatroSolver::solveForRotation(const Mat3X&, const Mat3X&, Eigen::Matrix3d*, BoolRow*) {
-  throw std::runtime_error("teaser (B200): stand-alone QuatroSolver::solveForRotation is not exposed; use solve()");
+void FastGlobalRegistrationSolver::solveForRotation(const Mat3X& src, const Mat3X& dst, Eigen::Matrix3d* rotation,
+                                                    BoolRow* inliers) {
+  rotation_via_abi(1, "FastGlobalRegistrationSolver::solveForRotation", params_, src, dst, rotation, inliers, &cost_);
+}
+void QuatroSolver::solveForRotation(const Mat3X& src, const Mat3X& dst, Eigen::Matrix3d* rotation, BoolRow* inliers) {
+  rotation_via_abi(2, "QuatroSolver::solveForRotation", params_, src, dst, rotation, inliers, &cost_);
 }
 
 // ------------------------------------------------------------------------------------------------ max clique

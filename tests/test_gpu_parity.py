@@ -694,3 +694,25 @@ def test_batch_c4_shape(ctx):
         assert np.array_equal(cl[b, :m], o["clique"])
         assert synth.angular_error(o["R"], capi.rotation_from_solution_record(sols[b])) <= ROT_TOL
         assert np.linalg.norm(o["t"] - sols[b]["translation"]) <= TRANS_TOL
+
+
+def test_standalone_rotation_backends_kat(ctx):
+    """FGR and Quatro on caller-supplied TIMs (rotation-solver-test.cc:23-135, registration-test.cc:144-218)."""
+    src = np.loadtxt(os.path.join(synth.GOLDEN_DIR, "registration_test", "rotation_only_src.csv"), delimiter=",")
+    Rexp = np.array([[0.997379773225804, -0.019905935977315, -0.069551000516966],
+                     [0.013777311189888, 0.996068297974922, -0.087510750572249],
+                     [0.071019530105605, 0.086323226782879, 0.993732623426126]])
+    g = ctx.rotation_solve(1, src, src @ Rexp.T, 1e-3, 1.4, 100, 1e-12)
+    o = orc.fgr(src, src @ Rexp.T, 100, 1e-12, 1.4, 1e-3)
+    assert synth.angular_error(Rexp, g["R"]) < 1e-5 and synth.angular_error(o["R"], g["R"]) < 1e-9
+    assert g["iterations"] == o["iterations"]
+    Ryaw = np.array([[0.997379773225804, -0.072343541246221, 0.0], [0.072343541246221, 0.997379773225804, 0.0],
+                     [0.0, 0.0, 1.0]])
+    g = ctx.rotation_solve(2, src, src @ Ryaw.T, 0.0067364, 1.4, 100, 0.005)
+    assert synth.angular_error(Ryaw, g["R"]) < 1e-5
+    rng = np.random.default_rng(3)
+    dst = src @ Ryaw.T
+    dst[:40] += rng.normal(size=(40, 3))
+    g = ctx.rotation_solve(2, src, dst, 0.01, 1.4, 100, 1e-9)
+    o = orc.quatro(src, dst, 100, 1e-9, 1.4, 0.01)
+    assert synth.angular_error(o["R"], g["R"]) < 1e-6 and np.mean(g["inliers"] != o["inliers"]) < 0.02
