@@ -1,0 +1,50 @@
+"""Exercise every kernel once on small inputs (meant to run under compute-sanitizer on the GPU box)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+capi = importlib.import_module("teaser-plusplus_b200.capi")
+synth = importlib.import_module("teaser-plusplus_b200.synth")
+
+ctx = capi.Context(0)
+pr = synth.config_problem("C2cube", 1, n=333)
+kw = dict(noise_bound=pr["noise_bound"], estimate_scaling=0, rotation_cost_threshold=1e-12)
+bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], 2 * pr["noise_bound"])
+for mode in (0, 1, 2):
+    c, proven = ctx.max_clique(bits, 333, mode=mode)
+    print("clique mode", mode, len(c), proven)
+for alg in (0, 1, 2):
+    for graph in (0, 1):
+        g = ctx.solve(pr["src"], pr["dst"], capi.default_params(rotation_estimation_algorithm=alg,
+                                                                rotation_tim_graph=graph, **kw))
+        print("solve alg", alg, "graph", graph, g["valid"], len(g["clique"]))
+g = ctx.solve(pr["src"][:120], pr["dst"][:120] * 1.5, capi.default_params(noise_bound=pr["noise_bound"], estimate_scaling=1))
+print("scale small", g["scale"])
+q = synth.make_problem(1600, 0.5, 5, "ball")
+g = ctx.solve(q["src"], q["dst"] * 2.0, capi.default_params(noise_bound=2 * q["noise_bound"], estimate_scaling=1))
+print("scale large", g["scale"], len(g["clique"]))
+g = ctx.solve(pr["src"], pr["dst"], capi.default_params(inlier_selection_mode=3, **kw))
+print("none mode", len(g["clique"]))
+prs = [synth.config_problem("C4", b, n=257) for b in range(70)]
+src = np.ascontiguousarray(np.stack([p["src"] for p in prs]))
+dst = np.ascontiguousarray(np.stack([p["dst"] for p in prs]))
+sols, cl = ctx.solve_batch_array(src, dst, capi.default_params(**dict(kw, noise_bound=prs[0]["noise_bound"])))
+print("batch", int(sols["valid"].sum()), "/ 70")
+rng = np.random.default_rng(0)
+A = np.triu(rng.uniform(size=(200, 200)) < 0.4, 1)
+A = A | A.T
+pad = np.zeros((200, 256), dtype=np.uint8)
+pad[:, :200] = A
+b2 = np.packbits(pad, axis=1, bitorder="little").view(np.uint64).reshape(200, 4)
+c, proven = ctx.max_clique(b2, 200, mode=0)
+print("random graph clique", len(c), proven)
+t, m = ctx.tls_translation(pr["src"][:50], pr["src"][:50] + 1.0, 0.01)
+e, i = ctx.scalar_tls([0.5, 1, 0.6, 0.7, 1.2], [0.9, 0.9, 0.4, 0.5, 0.4])
+r = ctx.rotation_solve(1, pr["src"][:60], pr["src"][:60], 0.01)
+print("stage calls ok", t, e)
+ctx.close()
+print("DONE")
