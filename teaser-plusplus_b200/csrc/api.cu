@@ -279,9 +279,16 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
 // read by the degree / clique kernels) stay resident in the 126 MB L2 instead of making a round trip through HBM.
 int l2_chunk(const tzr_ctx* ctx, int B, int n, const tzr_params& p) {
   (void)ctx;
-  if (p.estimate_scaling) return B;  // per-launch scratch of the scale stage
+  // Optional sub-chunking of graph+degree so the degree pass reads the bitsets from L2 (TZR_L2_CHUNK_MB = MB of
+  // adjacency per sub-chunk).  Off by default: with the v5 graph kernel the tail of each small launch costs more
+  // than the saved HBM read (measured r01: 84.5 K reg/s unchunked vs 78.1 K at 96 MB, profiles/README.md).
+  static const long long budget_mb = [] {
+    const char* e = std::getenv("TZR_L2_CHUNK_MB");
+    return e ? std::atoll(e) : 0LL;
+  }();
+  if (budget_mb <= 0 || p.estimate_scaling) return B;
   const size_t per = (size_t)n * pitch64(n) * 8;
-  long long c = (long long)((size_t)96 << 20) / (long long)std::max<size_t>(per, 1);
+  long long c = (long long)((size_t)budget_mb << 20) / (long long)std::max<size_t>(per, 1);
   if (c < 1) c = 1;
   if (c >= B) return B;
   return (int)c;
@@ -348,9 +355,7 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
   cudaEventRecord(ev[1], st);
   int nl = 0;
   if (mode != 3) {
-    // graph + degree in L2-sized sub-chunks: the row popcounts then read the freshly written bitsets from the
-    // 126 MB L2 instead of HBM (the degree pass is otherwise a full second trip over B * n^2/8 bytes).  The
-    // graph event therefore covers both kernels; the tile kernel's own share is reported by the ncu launch list.
+    // graph + degree, optionally in L2-sized sub-chunks (see l2_chunk); the graph kernel has its own event pair.
     const int gch = l2_chunk(ctx, bt.B, bt.n, p);
     for (int b0 = 0; b0 < bt.B; b0 += gch) {
       Batch sb = (gch < bt.B) ? sub_batch(bt, b0, std::min(gch, bt.B - b0)) : bt;
@@ -379,8 +384,10 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
 }
 
 // Run the pipeline chunk by chunk on the compute stream.  ready[c] (optional) is an event the chunk's inputs wait for.
-int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, int chunk, const cudaEvent_t* ready) {
-  const int n_chunks = (bt.B + chunk - 1) / chunk;
+// bounds = n_chunks+1 ascending problem offsets (bounds[0] = 0, bounds[n_chunks] = B).
+int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<int>& bounds,
+                const cudaEvent_t* ready) {
+  const int n_chunks = (int)bounds.size() - 1;
   ctx->graph_ev_used = 0;
   while ((int)ctx->stage_ev.size() < 5 * n_chunks) {
     cudaEvent_t e;
@@ -395,7 +402,7 @@ int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, int chunk, const c
     if (cudaStreamWaitEvent(ctx->stream2, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
   }
   for (int c = 0; c < n_chunks; ++c) {
-    const int b0 = c * chunk, Bc = std::min(chunk, bt.B - b0);
+    const int b0 = bounds[c], Bc = bounds[c + 1] - b0;
     cudaStream_t st = (two && (c & 1)) ? ctx->stream2 : ctx->stream;
     if (ready) {
       if (cudaStreamWaitEvent(st, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
@@ -754,7 +761,7 @@ int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, co
   if (rc) return rc;
   bt.src = src_dev;
   bt.dst = dst_dev;
-  rc = run_chunked(ctx, bt, *params, B, nullptr);
+  rc = run_chunked(ctx, bt, *params, std::vector<int>{0, B}, nullptr);
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(solutions_dev, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToDevice, st));
@@ -801,10 +808,21 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
     hs = h_src;
     hd = h_dst;
   }
-  // Chunked pipeline: the H2D copy of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream).
-  int chunk = B;
-  if (B >= 64 && !params->estimate_scaling) chunk = std::max(32, B / 8);
-  const int n_chunks = (B + chunk - 1) / chunk;
+  // Chunked pipeline: the H2D copy of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute streams).
+  // PCIe moves a problem ~3x faster than the kernels consume it, so only the first chunk's copy is exposed: it is
+  // kept small (B/32) and the later chunks grow (3B/32, B/8, then B/4 each) to keep launch tails few.
+  std::vector<int> bounds{0};
+  if (B >= 64 && !params->estimate_scaling) {
+    const int unit = std::max(8, B / 32);
+    const int sizes[3] = {unit, 3 * unit, 4 * unit};
+    for (int k = 0; bounds.back() < B; ++k) {
+      const int sz = k < 3 ? sizes[k] : 8 * unit;
+      bounds.push_back(std::min(B, bounds.back() + sz));
+    }
+  } else {
+    bounds.push_back(B);
+  }
+  const int n_chunks = (int)bounds.size() - 1;
   while ((int)ctx->chunk_ev.size() < n_chunks + 1) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -817,14 +835,14 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
     CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[n_chunks], 0));
   }
   for (int c = 0; c < n_chunks; ++c) {
-    const int b0 = c * chunk, Bc = std::min(chunk, B - b0);
+    const int b0 = bounds[c], Bc = bounds[c + 1] - b0;
     CK(cudaMemcpyAsync((void*)(bt.src + (size_t)b0 * n * 3), (const char*)hs + per * b0, per * Bc,
                        cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync((void*)(bt.dst + (size_t)b0 * n * 3), (const char*)hd + per * b0, per * Bc,
                        cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) CK(cudaEventRecord(ctx->chunk_ev[c], cs));
   }
-  rc = run_chunked(ctx, bt, *params, chunk, n_chunks > 1 ? ctx->chunk_ev.data() : nullptr);
+  rc = run_chunked(ctx, bt, *params, bounds, n_chunks > 1 ? ctx->chunk_ev.data() : nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

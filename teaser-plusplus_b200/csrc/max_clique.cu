@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(kHeurThreads) clique_heur_kernel(Batch bt) {
       }
     }
     __syncthreads();
-    if (s_nuni) continue;  // thinned: recompute degrees on the smaller P
+    // volatile: keeps the compiler from fusing this load with the adjacent s_csz into one LDS.64 executed by all
+    // threads (harmless, but racecheck flags it against thread 0's s_csz store below)
+    if (*(volatile int*)&s_nuni) continue;  // thinned: recompute degrees on the smaller P
     const int u = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
     if (tid == 0) {
       const int pos = s_csz;
