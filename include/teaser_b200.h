@@ -141,6 +141,26 @@ int tzr_tls_translation(tzr_ctx* ctx, const double* src_3xM, const double* dst_3
 int tzr_scalar_tls(tzr_ctx* ctx, const double* x, const double* ranges, int64_t m, double* estimate,
                    uint8_t* inliers);
 
+/* ---- upstream of solve(): correspondence generation ------------------------------------------
+ * Replaces Matcher::calculateCorrespondences (teaser/src/matcher.cc:21-53 -> normalizePoints :55-113 and
+ * advancedMatching :114-297).  Host pointers.  src_pts/dst_pts: ns x 3 / nd x 3 float xyz (PointXYZ AoS,
+ * geometry.h:15-24); src_feat/dst_feat: row-major ns x dim / nd x dim float descriptors (FPFH: dim = 33,
+ * pcl::FPFHSignature33::histogram), 1 <= dim <= 128.  The nearest-neighbour search is exact under
+ * flann::L2<float> (what KDTreeSingleIndex with eps = 0 returns), lowest index among equal distances.
+ * use_tuple_test + tuple_scale != 0 runs 100 * ncorr trials (:236); the reference seeds rand() with time(NULL),
+ * here the draws are splitmix64(tuple_seed + 3 t + k) >> 33 so a seed reproduces a run.
+ * pairs: capacity x 2 int32 rows (source index, target index), sorted and unique like the reference's output;
+ * capacity >= ns + nd is always enough.  global_scale (optional) receives Matcher::global_scale_. */
+int tzr_match_correspondences(tzr_ctx* ctx, const float* src_pts, int ns, const float* dst_pts, int nd,
+                              const float* src_feat, const float* dst_feat, int dim, int use_absolute_scale,
+                              int use_crosscheck, int use_tuple_test, float tuple_scale, uint64_t tuple_seed,
+                              int32_t* pairs, int64_t capacity, int64_t* n_pairs, float* global_scale);
+
+/* The matcher's search primitive on its own (Matcher::searchKDTree with nn = 1, matcher.cc:314-335, for every
+ * query row): nn_index[q] = argmin_i L2(query[q], db[i]), nn_dist[q] (optional) the squared distance. */
+int tzr_feature_nn(tzr_ctx* ctx, const float* query, int nq, const float* db, int ndb, int dim, int32_t* nn_index,
+                   float* nn_dist);
+
 /* ---- whole path -----------------------------------------------------------------------------
  * Replaces RobustRegistrationSolver::solve(src, dst) (registration.cc:568-737) for one problem
  * (tzr_solve) or B independent problems (tzr_solve_batch).  All intermediates stay on the device.

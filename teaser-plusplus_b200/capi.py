@@ -82,6 +82,7 @@ _SYMBOLS = [
     "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_rotation_solve", "tzr_tls_translation", "tzr_scalar_tls",
     "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
     "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks", "tzr_ctx_debug_counters",
+    "tzr_match_correspondences", "tzr_feature_nn",
 ]
 
 
@@ -136,6 +137,10 @@ def lib():
     L.tzr_ctx_filter_rechecks.argtypes = [vp]
     L.tzr_ctx_filter_rechecks.restype = C.c_int64
     L.tzr_ctx_debug_counters.argtypes = [vp, i64p]
+    fp = C.POINTER(C.c_float)
+    L.tzr_match_correspondences.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_float, C.c_uint64, i32p, C.c_int64, i64p, fp]
+    L.tzr_feature_nn.argtypes = [vp, fp, C.c_int, fp, C.c_int, C.c_int, i32p, fp]
     for s in _SYMBOLS:
         getattr(L, s)  # raises AttributeError if the header and the library disagree
     _lib = L
@@ -273,6 +278,43 @@ class Context:
         self._ck(lib().tzr_scalar_tls(self._h, _p(x, C.c_double), _p(r, C.c_double), x.size, C.byref(est),
                                       _p(inl, C.c_uint8)))
         return est.value, inl.astype(bool)
+
+    # -- upstream of solve(): Matcher::calculateCorrespondences (matcher.cc:21-337)
+    def match_correspondences(self, src_pts, dst_pts, src_feat, dst_feat, use_absolute_scale=True,
+                              use_crosscheck=True, use_tuple_test=True, tuple_scale=0.0, tuple_seed=0,
+                              return_scale=False):
+        """Same argument order and defaults as the reference method (matcher.h:39-43); points are (n,3) float32,
+        features (n,dim) float32.  Returns an (m,2) int32 array of sorted unique (source, target) index pairs."""
+        sp = np.ascontiguousarray(src_pts, dtype=np.float32)
+        tp = np.ascontiguousarray(dst_pts, dtype=np.float32)
+        sf = np.ascontiguousarray(src_feat, dtype=np.float32)
+        tf = np.ascontiguousarray(dst_feat, dtype=np.float32)
+        ns, nd = sp.shape[0], tp.shape[0]
+        if sp.shape != (ns, 3) or tp.shape != (nd, 3) or sf.ndim != 2 or tf.ndim != 2 or sf.shape[0] != ns or \
+                tf.shape[0] != nd or sf.shape[1] != tf.shape[1]:
+            raise TzrError("match_correspondences: points must be (n,3) and features (n,dim) with one row per point")
+        cap = ns + nd
+        pairs = np.zeros((cap, 2), dtype=np.int32)
+        cnt = C.c_int64()
+        g = C.c_float()
+        self._ck(lib().tzr_match_correspondences(
+            self._h, _p(sp, C.c_float), ns, _p(tp, C.c_float), nd, _p(sf, C.c_float), _p(tf, C.c_float), sf.shape[1],
+            int(bool(use_absolute_scale)), int(bool(use_crosscheck)), int(bool(use_tuple_test)), float(tuple_scale),
+            int(tuple_seed), _p(pairs, C.c_int32), cap, C.byref(cnt), C.byref(g)))
+        out = pairs[:cnt.value].copy()
+        return (out, g.value) if return_scale else out
+
+    def feature_nn(self, query, db):
+        """Exact 1-NN (flann::L2<float> accumulation order, lowest index among ties) of every query row in db."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        d = np.ascontiguousarray(db, dtype=np.float32)
+        if q.ndim != 2 or d.ndim != 2 or q.shape[1] != d.shape[1]:
+            raise TzrError("feature_nn: query and db must be (n,dim) with equal dim")
+        idx = np.zeros(q.shape[0], dtype=np.int32)
+        dist = np.zeros(q.shape[0], dtype=np.float32)
+        self._ck(lib().tzr_feature_nn(self._h, _p(q, C.c_float), q.shape[0], _p(d, C.c_float), d.shape[0], q.shape[1],
+                                      _p(idx, C.c_int32), _p(dist, C.c_float)))
+        return idx, dist
 
     # -- whole path
     def solve(self, src, dst, params: Params):

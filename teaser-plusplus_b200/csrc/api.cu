@@ -26,7 +26,7 @@ struct tzr_ctx {
   int num_sms = 148;
   // device buffers (grow-only)
   DevBuf src, dst, sf, df, pk, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
-      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx;
+      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx, m_in, m_scratch, m_out;
   // pinned host staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -499,7 +499,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->tstart, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
-                    &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx};
+                    &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx, &ctx->m_in, &ctx->m_scratch, &ctx->m_out};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -916,6 +916,92 @@ int tzr_last_graph(tzr_ctx* ctx, int b, uint64_t* adj_bits, int32_t* degree) {
                          (size_t)words64(n) * 8, n, cudaMemcpyDeviceToHost, st));
   if (degree) CK(cudaMemcpyAsync(degree, bt.deg + (size_t)b * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return TZR_OK;
+}
+
+int tzr_match_correspondences(tzr_ctx* ctx, const float* src_pts, int ns, const float* dst_pts, int nd,
+                              const float* src_feat, const float* dst_feat, int dim, int use_absolute_scale,
+                              int use_crosscheck, int use_tuple_test, float tuple_scale, uint64_t tuple_seed,
+                              int32_t* pairs, int64_t capacity, int64_t* n_pairs, float* global_scale) {
+  if (!ctx || !src_pts || !dst_pts || !src_feat || !dst_feat || !pairs || !n_pairs || ns <= 0 || nd <= 0 ||
+      dim < 1 || dim > kMatchMaxDim || capacity < 0)
+    return TZR_ERR_INVALID_ARG;
+  if ((long long)ns + nd > (1ll << 30)) return TZR_ERR_TOO_LARGE;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t pb_s = (size_t)ns * 3 * 4, pb_d = (size_t)nd * 3 * 4, fb_s = (size_t)ns * dim * 4,
+               fb_d = (size_t)nd * dim * 4;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  int rc;
+  if ((rc = ensure(ctx, ctx->m_in, al(pb_s) + al(pb_d) + al(fb_s) + al(fb_d))) != TZR_OK) return rc;
+  if ((rc = ensure(ctx, ctx->m_scratch, match_scratch_bytes(ns, nd))) != TZR_OK) return rc;
+  const size_t cap = (size_t)ns + nd;
+  if ((rc = ensure(ctx, ctx->m_out, cap * 8 + 256)) != TZR_OK) return rc;
+  char* in = (char*)ctx->m_in.p;
+  float* d_sp = (float*)in;
+  float* d_dp = (float*)(in + al(pb_s));
+  float* d_sf = (float*)(in + al(pb_s) + al(pb_d));
+  float* d_df = (float*)(in + al(pb_s) + al(pb_d) + al(fb_s));
+  int32_t* d_pairs = (int32_t*)ctx->m_out.p;
+  int* d_count = (int*)((char*)ctx->m_out.p + cap * 8);
+  float* d_g = (float*)(d_count + 1);
+  CK(cudaMemcpyAsync(d_sp, src_pts, pb_s, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_dp, dst_pts, pb_d, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_sf, src_feat, fb_s, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_df, dst_feat, fb_d, cudaMemcpyHostToDevice, st));
+  const int nl = launch_match(d_sp, ns, d_dp, nd, d_sf, d_df, dim, use_absolute_scale, use_crosscheck,
+                              use_tuple_test, tuple_scale, tuple_seed, ctx->m_scratch.p, d_pairs, d_count, d_g,
+                              ctx->num_sms, st);
+  if (nl < 0) return nl;
+  ctx->launches += nl;
+  if ((rc = check_launch(ctx, "matcher launch")) != TZR_OK) return rc;
+  struct {
+    int count;
+    float g;
+  } tail;
+  CK(cudaMemcpyAsync(&tail, d_count, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_pairs = tail.count;
+  if (global_scale) *global_scale = tail.g;
+  if ((int64_t)tail.count > capacity) {
+    ctx->last_error = "pairs capacity too small";
+    return TZR_ERR_INVALID_ARG;
+  }
+  if (tail.count > 0) {
+    CK(cudaMemcpyAsync(pairs, d_pairs, (size_t)tail.count * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return TZR_OK;
+}
+
+int tzr_feature_nn(tzr_ctx* ctx, const float* query, int nq, const float* db, int ndb, int dim, int32_t* nn_index,
+                   float* nn_dist) {
+  if (!ctx || !query || !db || !nn_index || nq <= 0 || ndb <= 0 || dim < 1 || dim > kMatchMaxDim)
+    return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t qb = (size_t)nq * dim * 4, dbb = (size_t)ndb * dim * 4;
+  int rc;
+  if ((rc = ensure(ctx, ctx->m_in, al(qb) + al(dbb))) != TZR_OK) return rc;
+  if ((rc = ensure(ctx, ctx->m_out, (size_t)nq * 8)) != TZR_OK) return rc;
+  float* d_q = (float*)ctx->m_in.p;
+  float* d_db = (float*)((char*)ctx->m_in.p + al(qb));
+  unsigned long long* d_best = (unsigned long long*)ctx->m_out.p;
+  CK(cudaMemcpyAsync(d_q, query, qb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_db, db, dbb, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_feature_nn(d_q, nq, d_db, ndb, dim, d_best, ctx->num_sms, st);
+  if ((rc = check_launch(ctx, "feature nn launch")) != TZR_OK) return rc;
+  std::vector<unsigned long long> h((size_t)nq);
+  CK(cudaMemcpyAsync(h.data(), d_best, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int q = 0; q < nq; ++q) {
+    nn_index[q] = (int32_t)(h[q] & 0xffffffffu);
+    if (nn_dist) {
+      const uint32_t bits = (uint32_t)(h[q] >> 32);
+      memcpy(&nn_dist[q], &bits, 4);
+    }
+  }
   return TZR_OK;
 }
 

@@ -23,6 +23,7 @@ constexpr int kTile = 128;          // graph tile edge (pairs per tile = 128*128
 constexpr int kGraphThreads = 128;  // 4 warps, each owns a 32x128 sub-tile (4 pairs per lane per step)
 constexpr int kHeurRoots = 4;       // heuristic start vertices per problem (top degrees); a global-peeling
                                     // second chance in the peel kernel covers the cases they all miss
+constexpr int kMatchMaxDim = 128;   // feature dimension limit of the matcher's NN kernel (FPFH: 33)
 constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memory clique kernels
 
 // Per-problem constants of the FP32 filter (see graph_build.cu).
@@ -122,5 +123,14 @@ void launch_translation_only(const double* src, const double* dst, int m, double
                              double* out_t, uint8_t* mask, cudaStream_t st);
 void launch_scalar_tls(const double* x, const double* ranges, long long m, double* skey, int32_t* sidx,
                        double* out_est, uint8_t* inliers, cudaStream_t st);
+
+// matcher.cu (Matcher::calculateCorrespondences, matcher.cc:21-337)
+int launch_feature_nn(const float* query, int nq, const float* db, int ndb, int dim, unsigned long long* best,
+                      int num_sms, cudaStream_t st);
+size_t match_scratch_bytes(int ns, int nd);
+int launch_match(float* src_pts, int ns, float* dst_pts, int nd, const float* src_feat, const float* dst_feat, int dim,
+                 int use_absolute_scale, int use_crosscheck, int use_tuple_test, float tuple_scale, uint64_t seed,
+                 void* scratch, int32_t* pairs, int* count, float* gscale, int num_sms, cudaStream_t st);
+
 
 }  // namespace tzr

@@ -1,0 +1,45 @@
+// Descriptor containers of the TEASER++ public API (mirrors teaser/include/teaser/fpfh.h:19-21 of the reference, where
+// FPFHCloud is pcl::PointCloud<pcl::FPFHSignature33>).  PCL is not a dependency of the B200 path: the two types below
+// have the layout the matcher needs (33 floats per point, `histogram` member like pcl::FPFHSignature33, a
+// std::vector-like cloud), so code that fills or iterates descriptors compiles unchanged.  Descriptor *estimation*
+// (FPFHEstimation::computeFPFHFeatures, fpfh.cc:15-43, a wrapper around PCL) is outside the hot path.
+#pragma once
+#include <cstddef>
+#include <memory>
+#include <vector>
+
+namespace teaser {
+
+struct FPFHSignature33 {
+  float histogram[33];
+  static int descriptorSize() { return 33; }
+};
+
+class FPFHCloud {
+ public:
+  using value_type = FPFHSignature33;
+  using storage = std::vector<FPFHSignature33>;
+  using iterator = storage::iterator;
+  using const_iterator = storage::const_iterator;
+
+  iterator begin() { return pts_.begin(); }
+  iterator end() { return pts_.end(); }
+  const_iterator begin() const { return pts_.begin(); }
+  const_iterator end() const { return pts_.end(); }
+  std::size_t size() const { return pts_.size(); }
+  bool empty() const { return pts_.empty(); }
+  void resize(std::size_t n) { pts_.resize(n); }
+  void reserve(std::size_t n) { pts_.reserve(n); }
+  void push_back(const FPFHSignature33& f) { pts_.push_back(f); }
+  void clear() { pts_.clear(); }
+  FPFHSignature33& operator[](std::size_t i) { return pts_[i]; }
+  const FPFHSignature33& operator[](std::size_t i) const { return pts_[i]; }
+  const float* data() const { return pts_.empty() ? nullptr : pts_[0].histogram; }  // size() x 33 row-major floats
+
+ private:
+  storage pts_;
+};
+
+using FPFHCloudPtr = std::shared_ptr<FPFHCloud>;
+
+}  // namespace teaser

@@ -149,3 +149,59 @@ def angular_error(Ra: np.ndarray, Rb: np.ndarray) -> float:
 
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+# ---------------------------------------------------------------------------------------------
+# Matcher inputs (Matcher::calculateCorrespondences, matcher.cc:21-53): points + per-point descriptors
+# ---------------------------------------------------------------------------------------------
+def random_fpfh(rng: np.random.Generator, n: int, dim: int = 33) -> np.ndarray:
+    """FPFH-shaped descriptors: non-negative float32, each 11-bin sub-histogram sums to 100 (pcl::FPFHSignature33)."""
+    f = rng.gamma(0.6, 1.0, size=(n, dim))
+    for lo in range(0, dim, 11):
+        blk = f[:, lo:lo + 11]
+        blk *= 100.0 / np.maximum(blk.sum(axis=1, keepdims=True), 1e-12)
+    return f.astype(np.float32)
+
+
+def matcher_problem(ns: int, nd: int, n_common: int, seed: int, dim: int = 33, feat_noise: float = 0.5,
+                    point_noise: float = 0.002):
+    """Two clouds that share n_common physical points.  Returns dict(src_pts, dst_pts (float32 (n,3)), src_feat,
+    dst_feat (float32 (n,dim)), R, t, true_pairs (n_common,2) int32 sorted by source index).  The shared points carry
+    the same descriptor up to feat_noise; the rest get unrelated descriptors."""
+    rng = np.random.default_rng(seed)
+    R = random_rotation(rng)
+    t = rng.uniform(-1, 1, size=3)
+    src = rng.uniform(0, 1, size=(ns, 3))
+    src_feat = random_fpfh(rng, ns, dim)
+    dst = R @ rng.uniform(0, 1, size=(nd, 3)).T
+    dst = dst.T + t
+    dst_feat = random_fpfh(rng, nd, dim)
+    si = np.sort(rng.permutation(ns)[:n_common])
+    di = rng.permutation(nd)[:n_common]
+    dst[di] = (R @ src[si].T).T + t + rng.normal(scale=point_noise, size=(n_common, 3))
+    dst_feat[di] = np.maximum(src_feat[si] + rng.normal(scale=feat_noise, size=(n_common, dim)), 0).astype(np.float32)
+    pairs = np.stack([si, di], axis=1).astype(np.int32)
+    return dict(src_pts=src.astype(np.float32), dst_pts=dst.astype(np.float32), src_feat=src_feat, dst_feat=dst_feat,
+                R=R, t=t, true_pairs=pairs)
+
+
+def read_pcd_ascii(path: str) -> np.ndarray:
+    """x y z rows of an ASCII .pcd (test/teaser/data/bunny.pcd)."""
+    rows, data = [], False
+    with open(path) as f:
+        for line in f:
+            if data:
+                v = line.split()
+                if len(v) >= 3:
+                    rows.append([float(v[0]), float(v[1]), float(v[2])])
+            elif line.startswith("DATA"):
+                data = True
+    return np.asarray(rows, dtype=np.float32)
+
+
+def bunny_fpfh():
+    """The reference's FPFH fixture: 397 bunny points and their 397x33 PCL descriptors (feature-test.cc:52-90)."""
+    pts = read_pcd_ascii(os.path.join(GOLDEN_DIR, "bunny.pcd"))
+    feat = np.loadtxt(os.path.join(GOLDEN_DIR, "bunny_fpfh.csv"), dtype=np.float32).reshape(-1, 33)
+    assert pts.shape[0] == feat.shape[0]
+    return pts, feat

@@ -9,4 +9,5 @@ for f in objectIn.csv sceneIn.csv rotation_only_src.csv translation_test_v1_inli
   cp "$REF/test/teaser/data/registration_test/$f" "$HERE/registration_test/"
 done
 cp "$REF/examples/example_data/bun_zipper_res3.ply" "$HERE/"
+cp "$REF/test/teaser/data/bunny.pcd" "$REF/test/teaser/data/bunny_fpfh.csv" "$HERE/"
 chmod -R u+w "$HERE"

@@ -91,8 +91,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    src = os.path.join(ORACLE_DIR, "teaser_oracle.cc")
-    if not os.path.exists(LIB_PATH) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(LIB_PATH)):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("teaser_oracle.cc", "matcher_oracle.cc")]
+    if not os.path.exists(LIB_PATH) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(LIB_PATH)
+                                           for f in srcs):
         build()
     L = C.CDLL(LIB_PATH)
     dp = C.POINTER(C.c_double)
@@ -123,6 +124,12 @@ def lib():
     L.orc_build_graph_bits.restype = C.c_int64
     L.orc_solve.argtypes = [C.POINTER(Params), dp, dp, C.c_int, C.POINTER(Solution), i32p, u8p, u8p, u64p, C.c_int]
     L.orc_solve.restype = C.c_int
+    fp = C.POINTER(C.c_float)
+    L.orc_match_correspondences.argtypes = [fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_float, C.c_uint64, i32p, C.c_int64, fp]
+    L.orc_match_correspondences.restype = C.c_int64
+    L.orc_nn1.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, i32p]
+    L.orc_nn1.restype = None
     _lib = L
     return L
 
@@ -290,4 +297,32 @@ def solve(src, dst, params, want_adj=False):
     out["rot_inliers"] = rot_mask[:nr].astype(bool)
     if want_adj:
         out["adj_bits"] = bits
+    return out
+
+
+def match_correspondences(src_pts, dst_pts, src_feat, dst_feat, use_absolute_scale=True, use_crosscheck=True,
+                          use_tuple_test=True, tuple_scale=0.0, tuple_seed=0, return_scale=False):
+    """Matcher::calculateCorrespondences restatement (oracle/matcher_oracle.cc)."""
+    sp = np.ascontiguousarray(src_pts, dtype=np.float32)
+    tp = np.ascontiguousarray(dst_pts, dtype=np.float32)
+    sf = np.ascontiguousarray(src_feat, dtype=np.float32)
+    tf = np.ascontiguousarray(dst_feat, dtype=np.float32)
+    ns, nd = sp.shape[0], tp.shape[0]
+    cap = ns + nd
+    pairs = np.zeros((cap, 2), dtype=np.int32)
+    g = C.c_float()
+    cnt = lib().orc_match_correspondences(_p(sp, C.c_float), ns, _p(tp, C.c_float), nd, _p(sf, C.c_float),
+                                          _p(tf, C.c_float), sf.shape[1], int(bool(use_absolute_scale)),
+                                          int(bool(use_crosscheck)), int(bool(use_tuple_test)), float(tuple_scale),
+                                          int(tuple_seed), _p(pairs, C.c_int32), cap, C.byref(g))
+    assert cnt >= 0
+    out = pairs[:cnt].copy()
+    return (out, g.value) if return_scale else out
+
+
+def nn1(query, db):
+    q = np.ascontiguousarray(query, dtype=np.float32)
+    d = np.ascontiguousarray(db, dtype=np.float32)
+    out = np.zeros(q.shape[0], dtype=np.int32)
+    lib().orc_nn1(_p(q, C.c_float), q.shape[0], _p(d, C.c_float), d.shape[0], q.shape[1], _p(out, C.c_int32))
     return out
