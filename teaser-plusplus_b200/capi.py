@@ -82,7 +82,7 @@ _SYMBOLS = [
     "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_rotation_solve", "tzr_tls_translation", "tzr_scalar_tls",
     "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
     "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks", "tzr_ctx_debug_counters",
-    "tzr_match_correspondences", "tzr_feature_nn",
+    "tzr_match_correspondences", "tzr_feature_nn", "tzr_compute_fpfh",
 ]
 
 
@@ -141,6 +141,7 @@ def lib():
     L.tzr_match_correspondences.argtypes = [vp, fp, C.c_int, fp, C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_uint64, i32p, C.c_int64, i64p, fp]
     L.tzr_feature_nn.argtypes = [vp, fp, C.c_int, fp, C.c_int, C.c_int, i32p, fp]
+    L.tzr_compute_fpfh.argtypes = [vp, fp, C.c_int, C.c_double, C.c_double, fp, fp]
     for s in _SYMBOLS:
         getattr(L, s)  # raises AttributeError if the header and the library disagree
     _lib = L
@@ -303,6 +304,17 @@ class Context:
             int(tuple_seed), _p(pairs, C.c_int32), cap, C.byref(cnt), C.byref(g)))
         out = pairs[:cnt.value].copy()
         return (out, g.value) if return_scale else out
+
+    def compute_fpfh(self, pts, normal_search_radius=0.03, fpfh_search_radius=0.05, return_normals=False):
+        """FPFHEstimation::computeFPFHFeatures (fpfh.h:39-41, same defaults): (n,3) float32 -> (n,33) float32."""
+        p = np.ascontiguousarray(pts, dtype=np.float32)
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise TzrError("compute_fpfh: points must be (n,3)")
+        out = np.zeros((p.shape[0], 33), dtype=np.float32)
+        nor = np.zeros((p.shape[0], 4), dtype=np.float32)
+        self._ck(lib().tzr_compute_fpfh(self._h, _p(p, C.c_float), p.shape[0], float(normal_search_radius),
+                                        float(fpfh_search_radius), _p(out, C.c_float), _p(nor, C.c_float)))
+        return (out, nor) if return_normals else out
 
     def feature_nn(self, query, db):
         """Exact 1-NN (flann::L2<float> accumulation order, lowest index among ties) of every query row in db."""

@@ -761,7 +761,16 @@ int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, co
   if (rc) return rc;
   bt.src = src_dev;
   bt.dst = dst_dev;
-  rc = run_chunked(ctx, bt, *params, std::vector<int>{0, B}, nullptr);
+  // Sub-batches alternate between the two compute streams: the latency-bound clique / rotation kernels of one
+  // sub-batch run under the issue-bound graph kernel of the next (TZR_DEV_CHUNKS overrides the count).
+  static const int dev_chunks = [] {
+    const char* e = std::getenv("TZR_DEV_CHUNKS");
+    return e ? std::max(1, atoi(e)) : 1;
+  }();
+  std::vector<int> bounds{0};
+  const int nch = (B >= 64 * dev_chunks && !params->estimate_scaling) ? dev_chunks : 1;
+  for (int c = 1; c <= nch; ++c) bounds.push_back((int)((long long)B * c / nch));
+  rc = run_chunked(ctx, bt, *params, bounds, nullptr);
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(solutions_dev, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToDevice, st));
@@ -970,6 +979,39 @@ int tzr_match_correspondences(tzr_ctx* ctx, const float* src_pts, int ns, const 
   if (tail.count > 0) {
     CK(cudaMemcpyAsync(pairs, d_pairs, (size_t)tail.count * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+  }
+  return TZR_OK;
+}
+
+int tzr_compute_fpfh(tzr_ctx* ctx, const float* pts, int n, double normal_search_radius, double fpfh_search_radius,
+                     float* fpfh_out, float* normals_out) {
+  if (!ctx || !pts || !fpfh_out || n <= 0 || !(normal_search_radius > 0) || !(fpfh_search_radius > 0))
+    return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t pb = (size_t)n * 12, nb = (size_t)n * 16, hb = (size_t)n * 33 * 4;
+  int rc;
+  if ((rc = ensure(ctx, ctx->m_in, al(pb))) != TZR_OK) return rc;
+  if ((rc = ensure(ctx, ctx->m_scratch, al(nb) + al(hb) + 256)) != TZR_OK) return rc;
+  if ((rc = ensure(ctx, ctx->m_out, al(hb))) != TZR_OK) return rc;
+  float* d_pts = (float*)ctx->m_in.p;
+  float4* d_normals = (float4*)ctx->m_scratch.p;
+  float* d_spfh = (float*)((char*)ctx->m_scratch.p + al(nb));
+  int* d_overflow = (int*)((char*)ctx->m_scratch.p + al(nb) + al(hb));
+  float* d_out = (float*)ctx->m_out.p;
+  CK(cudaMemcpyAsync(d_pts, pts, pb, cudaMemcpyHostToDevice, st));
+  ctx->launches += launch_fpfh(d_pts, n, normal_search_radius, fpfh_search_radius, d_normals, d_spfh, d_out,
+                               d_overflow, st);
+  if ((rc = check_launch(ctx, "fpfh launch")) != TZR_OK) return rc;
+  int overflow = 0;
+  CK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(fpfh_out, d_out, hb, cudaMemcpyDeviceToHost, st));
+  if (normals_out) CK(cudaMemcpyAsync(normals_out, d_normals, nb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (overflow) {
+    ctx->last_error = "a point has more than 4096 neighbours inside a search radius";
+    return TZR_ERR_TOO_LARGE;
   }
   return TZR_OK;
 }

@@ -124,6 +124,10 @@ void launch_translation_only(const double* src, const double* dst, int m, double
 void launch_scalar_tls(const double* x, const double* ranges, long long m, double* skey, int32_t* sidx,
                        double* out_est, uint8_t* inliers, cudaStream_t st);
 
+// fpfh.cu (FPFHEstimation::computeFPFHFeatures, fpfh.cc:15-43)
+int launch_fpfh(const float* pts, int n, double normal_radius, double fpfh_radius, float4* normals, float* spfh,
+                float* out, int* overflow, cudaStream_t st);
+
 // matcher.cu (Matcher::calculateCorrespondences, matcher.cc:21-337)
 int launch_feature_nn(const float* query, int nq, const float* db, int ndb, int dim, unsigned long long* best,
                       int num_sms, cudaStream_t st);

@@ -4,7 +4,9 @@
 // the B200 path, so the descriptors come from a file: the reference's own fixture test/teaser/data/bunny_fpfh.csv
 // (PCL FPFH of bunny.pcd); the target cloud is the transformed, shuffled, noisy source with 30 % of its descriptors
 // replaced by other points' descriptors (wrong matches).
-//   usage: example_cpp_fpfh <bunny.pcd> <bunny_fpfh.csv>
+// With only the .pcd argument the descriptors of both clouds are computed with teaser::FPFHEstimation, exactly as the
+// reference example does (teaser_cpp_fpfh.cc:86-89).
+//   usage: example_cpp_fpfh <bunny.pcd> [<bunny_fpfh.csv>]
 #include <chrono>
 #include <cmath>
 #include <fstream>
@@ -20,10 +22,11 @@
 constexpr double NOISE_BOUND = 0.001;
 
 int main(int argc, char** argv) {
-  if (argc < 3) {
-    std::cerr << "usage: " << argv[0] << " bunny.pcd bunny_fpfh.csv\n";
+  if (argc < 2) {
+    std::cerr << "usage: " << argv[0] << " bunny.pcd [bunny_fpfh.csv]\n";
     return 2;
   }
+  const bool from_file = argc >= 3;
   teaser::PointCloud src_cloud;
   {
     std::ifstream f(argv[1]);
@@ -41,7 +44,7 @@ int main(int argc, char** argv) {
   }
   const int N = static_cast<int>(src_cloud.size());
   teaser::FPFHCloud obj_descriptors;
-  {
+  if (from_file) {
     std::ifstream f(argv[2]);
     obj_descriptors.resize(N);
     for (int i = 0; i < N; ++i)
@@ -70,10 +73,18 @@ int main(int argc, char** argv) {
     double q[3];
     for (int r = 0; r < 3; ++r) q[r] = R(r, 0) * p.x + R(r, 1) * p.y + R(r, 2) * p.z + t(r) + noise(gen) * NOISE_BOUND / 2;
     tgt_cloud.push_back({static_cast<float>(q[0]), static_cast<float>(q[1]), static_cast<float>(q[2])});
-    const bool wrong = j % 10 < 3;
-    teaser::FPFHSignature33 d = obj_descriptors[wrong ? pick(gen) : perm[j]];
-    if (wrong) d.histogram[j % 33] += 0.5f;  // keep the wrong descriptor from being an exact duplicate
-    scene_descriptors.push_back(d);
+    if (from_file) {
+      const bool wrong = j % 10 < 3;
+      teaser::FPFHSignature33 d = obj_descriptors[wrong ? pick(gen) : perm[j]];
+      if (wrong) d.histogram[j % 33] += 0.5f;  // keep the wrong descriptor from being an exact duplicate
+      scene_descriptors.push_back(d);
+    }
+  }
+  if (!from_file) {
+    // Compute FPFH (teaser_cpp_fpfh.cc:86-89; radii scaled to this 397-point cloud)
+    teaser::FPFHEstimation fpfh;
+    obj_descriptors = *fpfh.computeFPFHFeatures(src_cloud, 0.03, 0.05);
+    scene_descriptors = *fpfh.computeFPFHFeatures(tgt_cloud, 0.03, 0.05);
   }
 
   // ---- the reference's matcher- and solver-facing code (teaser_cpp_fpfh.cc:91-113)

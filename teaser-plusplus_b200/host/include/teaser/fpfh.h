@@ -1,12 +1,16 @@
 // Descriptor containers of the TEASER++ public API (mirrors teaser/include/teaser/fpfh.h:19-21 of the reference, where
 // FPFHCloud is pcl::PointCloud<pcl::FPFHSignature33>).  PCL is not a dependency of the B200 path: the two types below
 // have the layout the matcher needs (33 floats per point, `histogram` member like pcl::FPFHSignature33, a
-// std::vector-like cloud), so code that fills or iterates descriptors compiles unchanged.  Descriptor *estimation*
-// (FPFHEstimation::computeFPFHFeatures, fpfh.cc:15-43, a wrapper around PCL) is outside the hot path.
+// std::vector-like cloud), so code that fills or iterates descriptors compiles unchanged.  FPFHEstimation keeps the
+// reference's computeFPFHFeatures / getNormals (fpfh.h:23-57); the work (PCL's NormalEstimationOMP + FPFHEstimationOMP
+// in the reference, fpfh.cc:15-43) runs on the GPU through tzr_compute_fpfh.  getImplPointer() (the raw PCL estimator)
+// has no counterpart.
 #pragma once
 #include <cstddef>
 #include <memory>
 #include <vector>
+
+#include "teaser/geometry.h"
 
 namespace teaser {
 
@@ -41,5 +45,32 @@ class FPFHCloud {
 };
 
 using FPFHCloudPtr = std::shared_ptr<FPFHCloud>;
+
+/// Layout-compatible stand-in for pcl::Normal's public fields.
+struct Normal {
+  float normal_x, normal_y, normal_z, curvature;
+};
+using NormalCloud = std::vector<Normal>;
+
+
+
+class FPFHEstimation {
+ public:
+  FPFHEstimation() = default;
+
+  /**
+   * Compute FPFH features (fpfh.h:39-41, same defaults).
+   * @param normal_search_radius Radius for estimating normals
+   * @param fpfh_search_radius Radius for calculating FPFH (needs to be at least normalSearchRadius)
+   */
+  FPFHCloudPtr computeFPFHFeatures(const PointCloud& input_cloud, double normal_search_radius = 0.03,
+                                   double fpfh_search_radius = 0.05);
+
+  /// The normal vectors of the input cloud that were used in the calculation of FPFH (fpfh.h:55).
+  NormalCloud getNormals() { return normals_; }
+
+ private:
+  NormalCloud normals_;
+};
 
 }  // namespace teaser

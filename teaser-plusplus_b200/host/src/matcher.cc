@@ -48,4 +48,23 @@ std::vector<std::pair<int, int>> Matcher::calculateCorrespondences(const PointCl
   return corres_;
 }
 
+FPFHCloudPtr FPFHEstimation::computeFPFHFeatures(const PointCloud& input_cloud, double normal_search_radius,
+                                                 double fpfh_search_radius) {
+  FPFHCloudPtr descriptors(new FPFHCloud());
+  normals_.clear();
+  const int n = static_cast<int>(input_cloud.size());
+  if (n == 0) return descriptors;
+  static_assert(sizeof(FPFHSignature33) == 33 * sizeof(float), "FPFHSignature33 must be 33 packed floats");
+  static_assert(sizeof(Normal) == 4 * sizeof(float), "Normal must be 4 packed floats");
+  descriptors->resize(n);
+  normals_.resize(n);
+  tzr_ctx* ctx = b200_context();
+  const int rc = tzr_compute_fpfh(ctx, &input_cloud[0].x, n, normal_search_radius, fpfh_search_radius,
+                                  (*descriptors)[0].histogram, &normals_[0].normal_x);
+  if (rc != TZR_OK)
+    throw std::runtime_error(std::string("teaser::FPFHEstimation (B200): ") + tzr_status_string(rc) + " (" +
+                             tzr_last_error(ctx) + ")");
+  return descriptors;
+}
+
 }  // namespace teaser

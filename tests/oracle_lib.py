@@ -91,7 +91,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("teaser_oracle.cc", "matcher_oracle.cc")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("teaser_oracle.cc", "matcher_oracle.cc", "fpfh_oracle.cc")]
     if not os.path.exists(LIB_PATH) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(LIB_PATH)
                                            for f in srcs):
         build()
@@ -130,6 +130,8 @@ def lib():
     L.orc_match_correspondences.restype = C.c_int64
     L.orc_nn1.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, i32p]
     L.orc_nn1.restype = None
+    L.orc_compute_fpfh.argtypes = [fp, C.c_int, C.c_double, C.c_double, C.c_int, fp, fp]
+    L.orc_compute_fpfh.restype = None
     _lib = L
     return L
 
@@ -326,3 +328,13 @@ def nn1(query, db):
     out = np.zeros(q.shape[0], dtype=np.int32)
     lib().orc_nn1(_p(q, C.c_float), q.shape[0], _p(d, C.c_float), d.shape[0], q.shape[1], _p(out, C.c_int32))
     return out
+
+
+def compute_fpfh(pts, normal_search_radius=0.03, fpfh_search_radius=0.05, cov_variant=0):
+    """FPFHEstimation::computeFPFHFeatures restatement (oracle/fpfh_oracle.cc). Returns (fpfh (n,33), normals (n,4))."""
+    p = np.ascontiguousarray(pts, dtype=np.float32)
+    out = np.zeros((p.shape[0], 33), dtype=np.float32)
+    nor = np.zeros((p.shape[0], 4), dtype=np.float32)
+    lib().orc_compute_fpfh(_p(p, C.c_float), p.shape[0], float(normal_search_radius), float(fpfh_search_radius),
+                           int(cov_variant), _p(nor, C.c_float), _p(out, C.c_float))
+    return out, nor
