@@ -170,6 +170,46 @@ int tzr_compute_fpfh(tzr_ctx* ctx, const float* pts, int n, double normal_search
 int tzr_feature_nn(tzr_ctx* ctx, const float* query, int nq, const float* db, int ndb, int dim, int32_t* nn_index,
                    float* nn_dist);
 
+/* ---- downstream of solve(): certification ------------------------------------------------------
+ * Replaces DRSCertifier::certify (teaser/src/certification.cc:40-190; Params certification.h:70-108).  Host pointers.
+ * R: 3x3 column-major rotation estimate; src/dst: 3 x N column-major (the TIMs the rotation was estimated from);
+ * theta: N doubles, +1 inlier / -1 outlier (the bool overload of the reference maps true -> +1, :22-38).
+ * traj (optional, capacity traj_capacity): the sub-optimality gap of every iteration
+ * (CertificationResult::suboptimality_traj).  eig_decomposition_solver is accepted for source compatibility; both
+ * values use the device eigensolver. */
+typedef struct tzr_certifier_params {
+  double noise_bound;     /* 0.01 */
+  double cbar2;           /* 1 */
+  double sub_optimality;  /* 1e-3 */
+  double max_iterations;  /* 2e2 (a double in the reference too) */
+  double gamma_tau;       /* 1.999999 */
+  int32_t eig_decomposition_solver; /* 0 EIGEN, 1 SPECTRA */
+  int32_t reserved;
+} tzr_certifier_params;
+
+typedef struct tzr_certification_result {
+  int32_t is_optimal;
+  int32_t n_iterations;        /* length of the trajectory */
+  double best_suboptimality;
+} tzr_certification_result;
+
+void tzr_certifier_params_default(tzr_certifier_params* p);
+
+int tzr_certify(tzr_ctx* ctx, const tzr_certifier_params* params, const double* R_colmajor9, const double* src_3xN,
+                const double* dst_3xN, const double* theta, int n, tzr_certification_result* result, double* traj,
+                int traj_capacity);
+
+/* Building blocks, exposed so that each can be checked against the reference's fixtures
+ * (test/teaser/certification-test.cc:355-497):
+ * tzr_certifier_initial_matrix: M_init = D^T Q_cost D - mu J - lambda_guess (certification.cc:60-100), dense
+ *   (4n+4)^2 column-major, and mu (:92) — covers getQCost, getBlockDiagOmega/getOmega1, getLambdaGuess.
+ * tzr_certifier_dual_projection: getOptimalDualProjection (:316-446) with getLinearProjection's inverse map (:531-655)
+ *   applied in closed form; W and W_dual are dense (4n+4)^2 column-major, theta as in tzr_certify. */
+int tzr_certifier_initial_matrix(tzr_ctx* ctx, const tzr_certifier_params* params, const double* R_colmajor9,
+                                 const double* src_3xN, const double* dst_3xN, const double* theta, int n,
+                                 double* M_init, double* mu);
+int tzr_certifier_dual_projection(tzr_ctx* ctx, const double* W, const double* theta, int n, double* W_dual);
+
 /* ---- whole path -----------------------------------------------------------------------------
  * Replaces RobustRegistrationSolver::solve(src, dst) (registration.cc:568-737) for one problem
  * (tzr_solve) or B independent problems (tzr_solve_batch).  All intermediates stay on the device.

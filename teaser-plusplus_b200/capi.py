@@ -76,13 +76,25 @@ assert SOLUTION_DTYPE.itemsize == C.sizeof(Solution), (SOLUTION_DTYPE.itemsize, 
 
 _lib = None
 
+class CertifierParams(C.Structure):
+    """tzr_certifier_params == DRSCertifier::Params (certification.h:70-108)."""
+    _fields_ = [("noise_bound", C.c_double), ("cbar2", C.c_double), ("sub_optimality", C.c_double),
+                ("max_iterations", C.c_double), ("gamma_tau", C.c_double), ("eig_decomposition_solver", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class CertificationResult(C.Structure):
+    _fields_ = [("is_optimal", C.c_int32), ("n_iterations", C.c_int32), ("best_suboptimality", C.c_double)]
+
+
 _SYMBOLS = [
     "tzr_abi_version", "tzr_status_string", "tzr_last_error", "tzr_params_default", "tzr_ctx_create",
     "tzr_ctx_destroy", "tzr_ctx_set_stream", "tzr_ctx_synchronize", "tzr_ctx_kernel_launches", "tzr_words_per_row",
     "tzr_graph_build", "tzr_max_clique", "tzr_gnc_tls_rotation", "tzr_rotation_solve", "tzr_tls_translation", "tzr_scalar_tls",
     "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
     "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks", "tzr_ctx_debug_counters",
-    "tzr_match_correspondences", "tzr_feature_nn", "tzr_compute_fpfh",
+    "tzr_match_correspondences", "tzr_feature_nn", "tzr_compute_fpfh", "tzr_certifier_params_default", "tzr_certify",
+    "tzr_certifier_initial_matrix", "tzr_certifier_dual_projection",
 ]
 
 
@@ -142,6 +154,12 @@ def lib():
                                             C.c_float, C.c_uint64, i32p, C.c_int64, i64p, fp]
     L.tzr_feature_nn.argtypes = [vp, fp, C.c_int, fp, C.c_int, C.c_int, i32p, fp]
     L.tzr_compute_fpfh.argtypes = [vp, fp, C.c_int, C.c_double, C.c_double, fp, fp]
+    L.tzr_certifier_params_default.argtypes = [C.POINTER(CertifierParams)]
+    L.tzr_certifier_params_default.restype = None
+    L.tzr_certify.argtypes = [vp, C.POINTER(CertifierParams), dp, dp, dp, dp, C.c_int, C.POINTER(CertificationResult),
+                              dp, C.c_int]
+    L.tzr_certifier_initial_matrix.argtypes = [vp, C.POINTER(CertifierParams), dp, dp, dp, dp, C.c_int, dp, dp]
+    L.tzr_certifier_dual_projection.argtypes = [vp, dp, dp, C.c_int, dp]
     for s in _SYMBOLS:
         getattr(L, s)  # raises AttributeError if the header and the library disagree
     _lib = L
@@ -279,6 +297,63 @@ class Context:
         self._ck(lib().tzr_scalar_tls(self._h, _p(x, C.c_double), _p(r, C.c_double), x.size, C.byref(est),
                                       _p(inl, C.c_uint8)))
         return est.value, inl.astype(bool)
+
+    # -- downstream of solve(): DRSCertifier (certification.cc)
+    @staticmethod
+    def _cert_inputs(R, src, dst, theta):
+        Rc = np.ascontiguousarray(np.asarray(R, dtype=np.float64).T)      # column-major 3x3
+        s = np.ascontiguousarray(np.asarray(src, dtype=np.float64).T)     # (3,N) -> N xyz triples == column-major 3xN
+        d = np.ascontiguousarray(np.asarray(dst, dtype=np.float64).T)
+        th = np.asarray(theta)
+        th = np.where(th, 1.0, -1.0) if th.dtype == np.bool_ else th.astype(np.float64)
+        th = np.ascontiguousarray(th.ravel())
+        if s.shape[1] != 3 or d.shape != s.shape or th.size != s.shape[0]:
+            raise TzrError("certify: src/dst must be (3,N) and theta (N,)")
+        return Rc, s, d, th
+
+    @staticmethod
+    def certifier_params(**kw) -> "CertifierParams":
+        p = CertifierParams()
+        lib().tzr_certifier_params_default(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        return p
+
+    def certify(self, R, src, dst, theta, **params):
+        """DRSCertifier(params).certify(R, src, dst, theta) (certification.cc:22-190); src/dst are (3,N)."""
+        p = self.certifier_params(**params)
+        Rc, s, d, th = self._cert_inputs(R, src, dst, theta)
+        cap = int(max(1, np.ceil(p.max_iterations)))
+        traj = np.zeros(cap)
+        res = CertificationResult()
+        self._ck(lib().tzr_certify(self._h, C.byref(p), _p(Rc, C.c_double), _p(s, C.c_double), _p(d, C.c_double),
+                                   _p(th, C.c_double), th.size, C.byref(res), _p(traj, C.c_double), cap))
+        return dict(is_optimal=bool(res.is_optimal), best_suboptimality=res.best_suboptimality,
+                    suboptimality_traj=traj[:res.n_iterations].copy())
+
+    def certifier_initial_matrix(self, R, src, dst, theta, **params):
+        p = self.certifier_params(**params)
+        Rc, s, d, th = self._cert_inputs(R, src, dst, theta)
+        n = 4 * th.size + 4
+        M = np.zeros((n, n))
+        mu = C.c_double()
+        self._ck(lib().tzr_certifier_initial_matrix(self._h, C.byref(p), _p(Rc, C.c_double), _p(s, C.c_double),
+                                                    _p(d, C.c_double), _p(th, C.c_double), th.size,
+                                                    _p(M, C.c_double), C.byref(mu)))
+        return M.T.copy(), mu.value      # column-major buffer -> numpy row-major view of the same matrix
+
+    def certifier_dual_projection(self, W, theta):
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).ravel())
+        Wc = np.ascontiguousarray(np.asarray(W, dtype=np.float64).T)
+        n = 4 * th.size + 4
+        if Wc.shape != (n, n):
+            raise TzrError("certifier_dual_projection: W must be (4N+4, 4N+4)")
+        out = np.zeros((n, n))
+        self._ck(lib().tzr_certifier_dual_projection(self._h, _p(Wc, C.c_double), _p(th, C.c_double), th.size,
+                                                     _p(out, C.c_double)))
+        return out.T.copy()
 
     # -- upstream of solve(): Matcher::calculateCorrespondences (matcher.cc:21-337)
     def match_correspondences(self, src_pts, dst_pts, src_feat, dst_feat, use_absolute_scale=True,

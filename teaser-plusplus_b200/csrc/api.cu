@@ -26,7 +26,7 @@ struct tzr_ctx {
   int num_sms = 148;
   // device buffers (grow-only)
   DevBuf src, dst, sf, df, pk, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
-      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx, m_in, m_scratch, m_out;
+      centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx, m_in, m_scratch, m_out, cert;
   // pinned host staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -499,7 +499,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->tstart, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
-                    &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx, &ctx->m_in, &ctx->m_scratch, &ctx->m_out};
+                    &ctx->misc, &ctx->sc_x, &ctx->sc_r, &ctx->sc_key, &ctx->sc_idx, &ctx->m_in, &ctx->m_scratch, &ctx->m_out, &ctx->cert};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -981,6 +981,55 @@ int tzr_match_correspondences(tzr_ctx* ctx, const float* src_pts, int ns, const 
     CK(cudaStreamSynchronize(st));
   }
   return TZR_OK;
+}
+
+void tzr_certifier_params_default(tzr_certifier_params* p) {
+  if (!p) return;
+  p->noise_bound = 0.01;      // certification.h:74
+  p->cbar2 = 1;               // :80
+  p->sub_optimality = 1e-3;   // :87
+  p->max_iterations = 2e2;    // :92
+  p->gamma_tau = 1.999999;    // :98
+  p->eig_decomposition_solver = 0;
+  p->reserved = 0;
+}
+
+int tzr_certify(tzr_ctx* ctx, const tzr_certifier_params* params, const double* R_colmajor9, const double* src_3xN,
+                const double* dst_3xN, const double* theta, int n, tzr_certification_result* result, double* traj,
+                int traj_capacity) {
+  if (!ctx || !params || !R_colmajor9 || !src_3xN || !dst_3xN || !theta || !result || n <= 0 || traj_capacity < 0)
+    return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  int opt = 0, iters = 0;
+  double best = 0;
+  const int rc = certify_device(0, params->noise_bound, params->cbar2, params->sub_optimality, params->max_iterations,
+                                params->gamma_tau, R_colmajor9, src_3xN, dst_3xN, theta, n, &opt, &best, &iters, traj,
+                                traj_capacity, nullptr, nullptr, nullptr, nullptr, &ctx->cert.p, &ctx->cert.cap,
+                                &ctx->launches, ctx->stream, &ctx->last_error);
+  if (rc != TZR_OK) return rc;
+  result->is_optimal = opt;
+  result->n_iterations = iters;
+  result->best_suboptimality = best;
+  return TZR_OK;
+}
+
+int tzr_certifier_initial_matrix(tzr_ctx* ctx, const tzr_certifier_params* params, const double* R_colmajor9,
+                                 const double* src_3xN, const double* dst_3xN, const double* theta, int n,
+                                 double* M_init, double* mu) {
+  if (!ctx || !params || !R_colmajor9 || !src_3xN || !dst_3xN || !theta || !M_init || !mu || n <= 0)
+    return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  return certify_device(1, params->noise_bound, params->cbar2, 0, 0, 0, R_colmajor9, src_3xN, dst_3xN, theta, n,
+                        nullptr, nullptr, nullptr, nullptr, 0, M_init, mu, nullptr, nullptr, &ctx->cert.p,
+                        &ctx->cert.cap, &ctx->launches, ctx->stream, &ctx->last_error);
+}
+
+int tzr_certifier_dual_projection(tzr_ctx* ctx, const double* W, const double* theta, int n, double* W_dual) {
+  if (!ctx || !W || !theta || !W_dual || n <= 0) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  return certify_device(2, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr, theta, n, nullptr, nullptr, nullptr, nullptr, 0,
+                        nullptr, nullptr, W, W_dual, &ctx->cert.p, &ctx->cert.cap, &ctx->launches, ctx->stream,
+                        &ctx->last_error);
 }
 
 int tzr_compute_fpfh(tzr_ctx* ctx, const float* pts, int n, double normal_search_radius, double fpfh_search_radius,

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <string>
+
 #include "../../include/teaser_b200.h"
 
 namespace tzr {
@@ -127,6 +129,13 @@ void launch_scalar_tls(const double* x, const double* ranges, long long m, doubl
 // fpfh.cu (FPFHEstimation::computeFPFHFeatures, fpfh.cc:15-43)
 int launch_fpfh(const float* pts, int n, double normal_radius, double fpfh_radius, float4* normals, float* spfh,
                 float* out, int* overflow, cudaStream_t st);
+
+// certify.cu (DRSCertifier::certify, certification.cc:40-190); mode 0 certify, 1 initial matrix, 2 dual projection
+int certify_device(int mode, double noise_bound, double cbar2, double sub_optimality, double max_iterations,
+                   double gamma_tau, const double* R_cm, const double* src, const double* dst, const double* theta,
+                   int N, int* is_optimal, double* best_subopt, int* n_iters, double* traj, int traj_cap,
+                   double* M_init_out, double* mu_out, const double* W_in, double* Wd_out, void** scratch,
+                   size_t* scratch_cap, int64_t* launches, cudaStream_t st, std::string* err);
 
 // matcher.cu (Matcher::calculateCorrespondences, matcher.cc:21-337)
 int launch_feature_nn(const float* query, int nq, const float* db, int ndb, int dim, unsigned long long* best,
