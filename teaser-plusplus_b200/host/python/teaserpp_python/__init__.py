@@ -1,10 +1,13 @@
 """`teaserpp_python` for the B200-native solve() path: same public names as the reference package
-(python/teaserpp_python/__init__.py); the certifier classes, which are not on the solve() path, are absent."""
+(python/teaserpp_python/__init__.py), certifier classes included."""
 from functools import wraps
 from typing import Callable, NamedTuple
 
 from ._teaserpp import (
     OMP_MAX_THREADS,
+    CertificationResult,
+    DRSCertifier,
+    EigSolverType,
     InlierGraphFormulation,
     InlierSelectionMode,
     RegistrationSolution,
@@ -16,6 +19,7 @@ from ._teaserpp import (
 RobustRegistrationSolver.ROTATION_ESTIMATION_ALGORITHM = RotationEstimationAlgorithm
 RobustRegistrationSolver.INLIER_SELECTION_MODE = InlierSelectionMode
 RobustRegistrationSolver.INLIER_GRAPH_FORMULATION = InlierGraphFormulation
+DRSCertifier.EIG_SOLVER_TYPE = EigSolverType
 
 
 class RobustRegistrationSolverParams(NamedTuple):

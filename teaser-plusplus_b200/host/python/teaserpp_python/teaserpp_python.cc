@@ -3,13 +3,14 @@
 // working; arrays cross the boundary as numpy (3,N) float64 exactly like the reference's pybind11/eigen.h casters
 // (copied if not Fortran-contiguous).  Fixes of the reference's copy-paste slips: the dst_* properties
 // return the dst getters, Params exposes max_clique_num_threads, the ctor default time limit is 3600.
-// The certifier classes (DRSCertifier, not on the solve() path) are not part of this module.
+// The certifier classes (EigSolverType, CertificationResult, DRSCertifier + Params, :71-74,249-291) are bound too.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
 #include <sstream>
 
+#include "teaser/certification.h"
 #include "teaser/registration.h"
 
 namespace py = pybind11;
@@ -191,4 +192,57 @@ PYBIND11_MODULE(_teaserpp, m) {
            << "\nmax_clique_time_limit=" << a.max_clique_time_limit << "\n>";
         return os.str();
       });
+
+  // ---- certifier (reference teaserpp_python.cc:71-74, 249-291)
+  using Cert = teaser::DRSCertifier;
+  py::enum_<Cert::EIG_SOLVER_TYPE>(m, "EigSolverType")
+      .value("EIGEN", Cert::EIG_SOLVER_TYPE::EIGEN)
+      .value("SPECTRA", Cert::EIG_SOLVER_TYPE::SPECTRA);
+
+  py::class_<teaser::CertificationResult>(m, "CertificationResult")
+      .def_readwrite("is_optimal", &teaser::CertificationResult::is_optimal)
+      .def_readwrite("best_suboptimality", &teaser::CertificationResult::best_suboptimality)
+      .def_readwrite("suboptimality_traj", &teaser::CertificationResult::suboptimality_traj)
+      .def("__repr__", [](const teaser::CertificationResult& a) {
+        std::ostringstream os;
+        os << "<CertificationResult \n"
+           << "Is optimal:" << a.is_optimal << "\n"
+           << "Best suboptimality:" << a.best_suboptimality << "\n"
+           << "Iterations: " << a.suboptimality_traj.size() << "\n"
+           << ">";
+        return os.str();
+      });
+
+  py::class_<Cert> certifier(m, "DRSCertifier");
+  auto to_r3 = [](const ArrD& R) {
+    if (R.ndim() != 2 || R.shape(0) != 3 || R.shape(1) != 3) throw std::invalid_argument("expected a (3, 3) rotation");
+    Eigen::Matrix3d m3;
+    std::memcpy(m3.data(), R.data(), sizeof(double) * 9);
+    return m3;
+  };
+  certifier.def(py::init<const Cert::Params>())
+      // one entry point for both reference overloads (bool mask / +-1 doubles): dispatching on the dtype here keeps
+      // pybind11's implicit array conversions from sending a float theta to the bool overload
+      .def("certify", [to_r3](Cert& c, const ArrD& R, const ArrD& src, const ArrD& dst, const py::array& theta) {
+        if (theta.dtype().kind() == 'b') {
+          auto tb = py::array_t<bool, py::array::c_style | py::array::forcecast>::ensure(theta);
+          Eigen::Matrix<bool, 1, Eigen::Dynamic> th(1, tb.size());
+          for (py::ssize_t i = 0; i < tb.size(); ++i) th(i) = tb.data()[i];
+          return c.certify(to_r3(R), to_mat3x(src), to_mat3x(dst), th);
+        }
+        auto td = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(theta);
+        if (!td) throw std::invalid_argument("theta must be a bool or float array");
+        Eigen::Matrix<double, 1, Eigen::Dynamic> th(1, td.size());
+        std::memcpy(th.data(), td.data(), sizeof(double) * static_cast<size_t>(td.size()));
+        return c.certify(to_r3(R), to_mat3x(src), to_mat3x(dst), th);
+      });
+
+  py::class_<Cert::Params>(certifier, "Params")
+      .def(py::init<>())
+      .def_readwrite("noise_bound", &Cert::Params::noise_bound)
+      .def_readwrite("cbar2", &Cert::Params::cbar2)
+      .def_readwrite("sub_optimality", &Cert::Params::sub_optimality)
+      .def_readwrite("max_iterations", &Cert::Params::max_iterations)
+      .def_readwrite("gamma_tau", &Cert::Params::gamma_tau)
+      .def_readwrite("eig_decomposition_solver", &Cert::Params::eig_decomposition_solver);
 }

@@ -107,3 +107,25 @@ def test_solve_then_certify_end_to_end(ctx):
     assert len(r["suboptimality_traj"]) == len(o["suboptimality_traj"])
     assert np.abs(r["suboptimality_traj"] - o["suboptimality_traj"]).max() < 1e-6 * max(1.0, o["suboptimality_traj"].max())
     assert r["is_optimal"] == o["is_optimal"]
+
+
+def test_pybind_certifier_matches_fixture():
+    """teaserpp_python.DRSCertifier (reference binding names, teaserpp_python.cc:249-291) through the C++ façade."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "teaser-plusplus_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host])
+    sys.path.insert(0, os.path.join(host, "python"))
+    import teaserpp_python as tpp
+    c = SMALL[0]
+    p = tpp.DRSCertifier.Params()
+    p.noise_bound = c["params"]["noise_bound"]
+    p.cbar2 = c["params"]["cbar2"]
+    p.eig_decomposition_solver = tpp.DRSCertifier.EIG_SOLVER_TYPE.EIGEN
+    cert = tpp.DRSCertifier(p)
+    r = cert.certify(c["R_est"], c["v1"], c["v2"], c["theta_est"])
+    assert np.abs(np.asarray(r.suboptimality_traj) - c["suboptimality_traj"]).max() < TOL
+    assert r.is_optimal and abs(r.best_suboptimality - c["suboptimality_traj"].min()) < TOL
+    r2 = cert.certify(c["R_est"], c["v1"], c["v2"], c["theta_est"] > 0)   # bool overload (certification.cc:22-38)
+    assert np.array_equal(np.asarray(r2.suboptimality_traj), np.asarray(r.suboptimality_traj))
+    assert "CertificationResult" in repr(r)
