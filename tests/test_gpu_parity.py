@@ -717,3 +717,51 @@ def test_standalone_rotation_backends_kat(ctx):
     g = ctx.rotation_solve(2, src, dst, 0.01, 1.4, 100, 1e-9)
     o = orc.quatro(src, dst, 100, 1e-9, 1.4, 0.01)
     assert synth.angular_error(o["R"], g["R"]) < 1e-6 and np.mean(g["inliers"] != o["inliers"]) < 0.02
+
+
+# ------------------------------------------------------------------ size edges
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_tiny_problems_match_oracle(ctx, n):
+    """n = 1 has no TIM at all, n = 2 a single one: validity and values must follow registration.cc:643-647."""
+    rng = np.random.default_rng(n)
+    R = synth.random_rotation(rng)
+    src = rng.uniform(size=(n, 3))
+    dst = (R @ src.T).T + 0.3
+    kw = fixed_params(0.01)
+    out = ctx.solve(src, dst, capi.default_params(**kw))
+    o = orc.solve(src, dst, orc.default_params(**kw))
+    assert out["valid"] == o["valid"]
+    assert np.array_equal(out["clique"], o["clique"])
+    if o["valid"]:
+        assert synth.angular_error(out["R"], o["R"]) < ROT_TOL
+        assert np.linalg.norm(out["t"] - o["t"]) < TRANS_TOL
+
+
+def test_maximum_size_problem(ctx):
+    """kMaxN = 32768 correspondences: graph properties + planted clique recovered; one more is TZR_ERR_TOO_LARGE."""
+    n = 32768
+    pr = synth.make_problem(n, 0.995, seed=7, model="ball", sigma=0.01, noise_bound=synth.NOISE_BOUND_SIGMA_001)
+    p = capi.default_params(**fixed_params(pr["noise_bound"]))
+    out = ctx.solve(pr["src"], pr["dst"], p)
+    assert out["valid"]
+    inl = np.sort(pr["inliers"])
+    assert len(out["clique"]) >= len(inl)
+    assert set(inl.tolist()) <= set(out["clique"].tolist())
+    assert synth.angular_error(out["R"], pr["R"]) < 0.02 and np.linalg.norm(out["t"] - pr["t"]) < 0.02
+    bits, deg = ctx.last_graph(0, n)
+    assert int(deg.sum()) == 2 * out["n_edges"]
+    rows = np.random.default_rng(0).integers(0, n, size=6)
+    # exact rows against a direct float64 evaluation of the predicate (registration.cc:427-443)
+    beta = 2 * pr["noise_bound"]
+    for r in rows:
+        ds = np.sqrt(((pr["src"] - pr["src"][r]) ** 2)[:, 0] + ((pr["src"] - pr["src"][r]) ** 2)[:, 1]
+                     + ((pr["src"] - pr["src"][r]) ** 2)[:, 2])
+        dd = np.sqrt(((pr["dst"] - pr["dst"][r]) ** 2)[:, 0] + ((pr["dst"] - pr["dst"][r]) ** 2)[:, 1]
+                     + ((pr["dst"] - pr["dst"][r]) ** 2)[:, 2])
+        want = np.abs(ds - dd) <= beta
+        want[r] = False
+        got = np.unpackbits(bits[r].view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert np.array_equal(got, want)
+    with pytest.raises(capi.TzrError):
+        big = np.zeros((n + 1, 3))
+        ctx.solve(big, big, p)
