@@ -46,5 +46,28 @@ t, m = ctx.tls_translation(pr["src"][:50], pr["src"][:50] + 1.0, 0.01)
 e, i = ctx.scalar_tls([0.5, 1, 0.6, 0.7, 1.2], [0.9, 0.9, 0.4, 0.5, 0.4])
 r = ctx.rotation_solve(1, pr["src"][:60], pr["src"][:60], 0.01)
 print("stage calls ok", t, e)
+# upstream / downstream stages
+mp = synth.matcher_problem(300, 260, 90, seed=3)
+for cc in (False, True):
+    for tt in (False, True):
+        pairs = ctx.match_correspondences(mp["src_pts"], mp["dst_pts"], mp["src_feat"], mp["dst_feat"], False, cc, tt,
+                                          0.95, tuple_seed=5)
+        print("matcher crosscheck", cc, "tuple", tt, len(pairs))
+idx, dist = ctx.feature_nn(mp["src_feat"], mp["dst_feat"])
+bp, _ = synth.bunny_fpfh()
+f, nrm = ctx.compute_fpfh(bp, 0.03, 0.05, return_normals=True)
+print("fpfh", f.shape, float(f.sum()))
+if "--no-cert" not in sys.argv:  # cuSOLVER's own kernels are slow under the sanitizer; ours are covered by the blocks
+    N = 12
+    v1 = rng.uniform(-1, 1, size=(3, N))
+    Rr = synth.random_rotation(rng)
+    v2 = Rr @ v1
+    th = np.ones(N)
+    th[-2:] = -1
+    v2[:, -2:] += 3.0
+    M0, mu = ctx.certifier_initial_matrix(Rr, v1, v2, th)
+    Wd = ctx.certifier_dual_projection(M0, th)
+    r = ctx.certify(Rr, v1, v2, th, max_iterations=3)
+    print("certify", mu, len(r["suboptimality_traj"]))
 ctx.close()
 print("DONE")
