@@ -38,8 +38,12 @@ struct tzr_ctx {
   int graph_ev_used = 0;
   std::vector<cudaEvent_t> stage_ev;  // 5 per chunk of the last pipelined call (stage timing is summed over chunks)
   int stage_chunks = 0;
-  cudaStream_t stream2 = nullptr;      // second compute stream: chunk tails overlap the next chunk's graph kernel
-  cudaEvent_t join_ev = nullptr;
+  // chunked batches run on two lanes: the issue-bound graph kernels queue back to back on the low-priority gstream,
+  // the latency-/HBM-bound degree, clique and rotation kernels of the previous chunk run on the high-priority hstream
+  // and slot into the SMs as graph CTAs retire
+  cudaStream_t gstream = nullptr, hstream = nullptr;
+  cudaEvent_t join_ev = nullptr, join_ev2 = nullptr;
+  std::vector<cudaEvent_t> gdone_ev;
   cudaStream_t copy_stream = nullptr;  // H2D of chunk k+1 overlaps the kernels of chunk k (host-pointer batches)
   std::vector<cudaEvent_t> chunk_ev;
 };
@@ -295,7 +299,11 @@ int l2_chunk(const tzr_ctx* ctx, int B, int n, const tzr_params& p) {
 }
 
 // The fused device pipeline for one uniform batch.  src/dst must already be set in bt.
-int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, cudaStream_t st) {
+// st: stream of the clique / rotation stages; sg: stream of prep + graph (== st for the single-lane form, otherwise
+// gdone is recorded on sg after the graph kernel and st waits for it).
+int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, cudaStream_t st,
+                 cudaStream_t sg = nullptr, cudaEvent_t gdone = nullptr) {
+  if (!sg) sg = st;
   if (p.rotation_estimation_algorithm < 0 || p.rotation_estimation_algorithm > 2 || p.rotation_tim_graph < 0 ||
       p.rotation_tim_graph > 1)
     return TZR_ERR_INVALID_ARG;
@@ -336,23 +344,23 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
     sckey = (double*)ctx->sc_key.p;
     scidx = (int32_t*)ctx->sc_idx.p;
   }
-  cudaEventRecord(ev[0], st);
-  init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(bt.sol, bt.B);
-  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 16 * sizeof(unsigned long long), st);
+  cudaEventRecord(ev[0], sg);
+  init_solutions_kernel<<<(bt.B + 127) / 128, 128, 0, sg>>>(bt.sol, bt.B);
+  if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 16 * sizeof(unsigned long long), sg);
   ctx->launches += 1;
   if (bt.scale_mode) {  // before prep: the FP32 filter copies are pre-scaled by the estimate
     bt.beta = 2.0 * p.noise_bound * std::sqrt(p.cbar2);
     if (scale_large) {
-      const int nl2 = launch_scale_estimation_large(bt, scx, scr, sckey, st);
+      const int nl2 = launch_scale_estimation_large(bt, scx, scr, sckey, sg);
       if (nl2 < 0) return TZR_ERR_TOO_LARGE;
       ctx->launches += nl2;
     } else {
-      ctx->launches += launch_scale_estimation(bt, scx, scr, sckey, scidx, sc_npad, st);
+      ctx->launches += launch_scale_estimation(bt, scx, scr, sckey, scidx, sc_npad, sg);
     }
   }
-  launch_prep(bt, st);
+  launch_prep(bt, sg);
   ctx->launches += 1;
-  cudaEventRecord(ev[1], st);
+  cudaEventRecord(ev[1], sg);
   int nl = 0;
   if (mode != 3) {
     // graph + degree, optionally in L2-sized sub-chunks (see l2_chunk); the graph kernel has its own event pair.
@@ -364,16 +372,24 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
         if (cudaEventCreate(&e) != cudaSuccess) return TZR_ERR_CUDA;
         ctx->graph_ev.push_back(e);
       }
-      cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used], st);
-      launch_graph(sb, st);
-      cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used + 1], st);
+      cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used], sg);
+      launch_graph(sb, sg);
+      cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used + 1], sg);
       ctx->graph_ev_used += 2;
+      if (sg != st) {  // two lanes (never combined with L2 sub-chunking: gch == B there)
+        cudaEventRecord(gdone, sg);
+        cudaStreamWaitEvent(st, gdone, 0);
+      }
       launch_degree(sb, st);
       nl += 2;
     }
     cudaEventRecord(ev[2], st);
     launch_clique(bt, p, mode, st, &nl);
   } else {
+    if (sg != st) {
+      cudaEventRecord(gdone, sg);
+      cudaStreamWaitEvent(st, gdone, 0);
+    }
     cudaEventRecord(ev[2], st);
   }
   cudaEventRecord(ev[3], st);
@@ -394,27 +410,34 @@ int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<
     if (cudaEventCreate(&e) != cudaSuccess) return TZR_ERR_CUDA;
     ctx->stage_ev.push_back(e);
   }
-  // chunks alternate between two compute streams (their scratch is disjoint): the latency-bound tail of chunk k
-  // (peel / exact / rot+trans on a few dozen CTAs) overlaps the graph kernel of chunk k+1
-  const bool two = n_chunks > 1 && ctx->stream2 != nullptr;
-  if (two) {
+  const bool lanes = n_chunks > 1 && ctx->gstream && ctx->hstream && l2_chunk(ctx, bt.B, bt.n, p) >= bt.B;
+  if (lanes) {
+    while ((int)ctx->gdone_ev.size() < n_chunks) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return TZR_ERR_CUDA;
+      ctx->gdone_ev.push_back(e);
+    }
     if (cudaEventRecord(ctx->join_ev, ctx->stream) != cudaSuccess) return TZR_ERR_CUDA;
-    if (cudaStreamWaitEvent(ctx->stream2, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
+    if (cudaStreamWaitEvent(ctx->gstream, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
+    if (cudaStreamWaitEvent(ctx->hstream, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
   }
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = bounds[c], Bc = bounds[c + 1] - b0;
-    cudaStream_t st = (two && (c & 1)) ? ctx->stream2 : ctx->stream;
+    cudaStream_t st = lanes ? ctx->hstream : ctx->stream;
+    cudaStream_t sg = lanes ? ctx->gstream : ctx->stream;
     if (ready) {
-      if (cudaStreamWaitEvent(st, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
+      if (cudaStreamWaitEvent(sg, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
     }
     Batch sb = (n_chunks > 1) ? sub_batch(bt, b0, Bc) : bt;
-    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * c, st);
+    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * c, st, sg, lanes ? ctx->gdone_ev[c] : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) bt = sb;  // keep fields filled in by run_pipeline (beta, scale_mode, ...)
   }
-  if (two) {  // everything later on ctx->stream (D2H, the caller's work) is ordered after stream2 as well
-    if (cudaEventRecord(ctx->join_ev, ctx->stream2) != cudaSuccess) return TZR_ERR_CUDA;
+  if (lanes) {  // everything later on ctx->stream (D2H, the caller's work) is ordered after both lanes
+    if (cudaEventRecord(ctx->join_ev, ctx->hstream) != cudaSuccess) return TZR_ERR_CUDA;
     if (cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0) != cudaSuccess) return TZR_ERR_CUDA;
+    if (cudaEventRecord(ctx->join_ev2, ctx->gstream) != cudaSuccess) return TZR_ERR_CUDA;
+    if (cudaStreamWaitEvent(ctx->stream, ctx->join_ev2, 0) != cudaSuccess) return TZR_ERR_CUDA;
   }
   ctx->stage_chunks = n_chunks;
   ctx->last = bt;
@@ -485,8 +508,14 @@ int tzr_ctx_create(int device, tzr_ctx** out) {
   }
   for (int i = 0; i < 5; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    cudaStreamCreateWithPriority(&ctx->gstream, cudaStreamNonBlocking, least);
+    cudaStreamCreateWithPriority(&ctx->hstream, cudaStreamNonBlocking, greatest);
+  }
   cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->join_ev2, cudaEventDisableTiming);
   *out = ctx;
   return TZR_OK;
 }
@@ -509,8 +538,11 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   for (cudaEvent_t e : ctx->stage_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->graph_ev) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
+  if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->join_ev2) cudaEventDestroy(ctx->join_ev2);
+  for (cudaEvent_t e : ctx->gdone_ev) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return TZR_OK;
@@ -612,7 +644,7 @@ int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, doub
   CK(cudaMemcpy2DAsync(bt.adj, (size_t)pitch64(n) * 8, adj_bits, (size_t)words64(n) * 8, (size_t)words64(n) * 8, n,
                        cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(bt.n_edges2, 0, sizeof(unsigned long long), st));
-  launch_degree(bt, st);
+  launch_degree(bt, st, true);
   tzr_params p;
   tzr_params_default(&p);
   p.kcore_heuristic_threshold = kcore_thr;

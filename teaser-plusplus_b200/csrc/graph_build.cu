@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     c.w = 0.f;
     sf[i] = a;
     df[i] = c;
+    bt.deg[(size_t)b * n + i] = 0;  // accumulated by the graph kernel (fused-degree path)
   }
   // pair-interleaved copy for the packed kernel: (point o, point o+32) of every 64-column half block adjacent
   const int npad = npad128(n);
@@ -578,7 +579,9 @@ struct __align__(16) IPointNeg2 {
   float4 c;  // (-dy,-dy,-dz,-dz)
 };
 
-template <bool kVerify, int kMinBlocks>
+// kFuseDeg: vertex degrees are accumulated here (row part: one atomic per row and strip; column part: one 32-lane
+// RED per transposed word) instead of a second pass over the B*n^2/8-byte bitset; deg[] is zeroed by prep_kernel.
+template <bool kVerify, int kMinBlocks, bool kFuseDeg>
 __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel(Batch bt) {
   const int b = blockIdx.y;
   const int n = bt.n;
@@ -628,6 +631,8 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel
 
   const int npadh = npad128(n) / 2;  // 64-bit elements per packed array
   const f32x2* pkp = reinterpret_cast<const f32x2*>(bt.pk + (size_t)b * 6 * npad128(n));
+  int* degp = bt.deg + (size_t)b * n;
+  int rdeg = 0;
   for (int J = J0; J < J1; ++J) {
     const int jb = J * kTile + lane;
     // column points, two pairs per 64-bit register: X[k] = (x of point jb+64k, x of point jb+64k+32), loaded as
@@ -733,12 +738,33 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel
     if (lane < nrows)
       *reinterpret_cast<uint4*>(adj32 + (size_t)(ibase + lane) * P32 + 4 * J) =
           make_uint4(roww[0], roww[1], roww[2], roww[3]);
+    if (kFuseDeg) rdeg += __popc(roww[0]) + __popc(roww[1]) + __popc(roww[2]) + __popc(roww[3]);
     if (I != J) {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (vj[c]) adj32[(size_t)(jb + 32 * c) * P32 + 4 * I + w] = colw[c];
+        if (vj[c]) {
+          adj32[(size_t)(jb + 32 * c) * P32 + 4 * I + w] = colw[c];
+          if (kFuseDeg && colw[c]) atomicAdd(degp + jb + 32 * c, __popc(colw[c]));
+        }
     }
     __syncwarp();
+  }
+  if (kFuseDeg && lane < nrows && rdeg) atomicAdd(degp + ibase + lane, rdeg);
+}
+
+// n_edges2[b] = sum of degrees (the fused-degree path has no degree kernel to do it)
+__global__ void __launch_bounds__(256) edge_count_kernel(Batch bt) {
+  const int b = blockIdx.x, n = bt.n;
+  __shared__ unsigned long long s_sum[8];
+  unsigned long long s = 0;
+  for (int v = threadIdx.x; v < n; v += 256) s += (unsigned long long)bt.deg[(size_t)b * n + v];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int q = 0; q < 8; ++q) t += s_sum[q];
+    bt.n_edges2[b] = t;
   }
 }
 
@@ -782,7 +808,7 @@ void launch_graph(const Batch& bt, cudaStream_t st) {
   }
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
   if (bt.flags_dbg & 2u)
-    graph_strip2_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    graph_strip2_kernel<true, 5, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
     graph_strip_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 32u)  // occupancy A/B: 5 CTAs/SM (96 registers)
@@ -790,12 +816,20 @@ void launch_graph(const Batch& bt, cudaStream_t st) {
   else if (bt.flags_dbg & 64u)  // scalar-FP32 strip kernel (A/B against the packed default)
     graph_strip_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 128u)  // packed kernel at 6 CTAs/SM
-    graph_strip2_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else  // default: packed FP32x2 strip kernel, 8 CTAs/SM
-    graph_strip2_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    graph_strip2_kernel<false, 6, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else if (bt.flags_dbg & 256u)  // degrees by the separate degree kernel (A/B against the fused default)
+    graph_strip2_kernel<false, 8, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else  // default: packed FP32x2 strip kernel, 8 CTAs/SM, degrees fused
+    graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
 }
 
-void launch_degree(const Batch& bt, cudaStream_t st) {
+bool graph_fuses_degrees(const Batch& bt) { return (bt.flags_dbg & (2u | 8u | 16u | 32u | 64u | 128u | 256u)) == 0; }
+
+void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only) {
+  if (!bitset_only && graph_fuses_degrees(bt)) {  // degrees were accumulated by the graph kernel; only the edge count is left
+    edge_count_kernel<<<bt.B, 256, 0, st>>>(bt);
+    return;
+  }
   dim3 grid((unsigned)((bt.n + 7) / 8), (unsigned)bt.B);
   degree_kernel<<<grid, 256, 0, st>>>(bt);
 }

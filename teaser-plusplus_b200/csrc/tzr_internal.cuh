@@ -106,7 +106,8 @@ __device__ __forceinline__ double tim_norm_exact(const double* __restrict__ p, i
 // kernels (defined in the .cu files) -------------------------------------------------------------
 void launch_prep(const Batch& bt, cudaStream_t st);
 void launch_graph(const Batch& bt, cudaStream_t st);
-void launch_degree(const Batch& bt, cudaStream_t st);
+// bitset_only: the adjacency did not come from launch_graph (tzr_max_clique on a caller's bitset): always popcount
+void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only = false);
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);
 int launch_scale_estimation(const Batch& bt, double* X, double* Rg, double* key, int32_t* idx, long long npad,
                             cudaStream_t st);
