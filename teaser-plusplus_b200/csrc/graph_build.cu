@@ -562,6 +562,11 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   f32x2 r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -664,8 +669,10 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel
         float a0, a1, c0, c1;
         upk2(a, a0, a1);
         upk2(bb, c0, c1);
-        const float x0 = fabsf(sqrt_approx(a0) - sqrt_approx(c0));
-        const float x1 = fabsf(sqrt_approx(a1) - sqrt_approx(c1));
+        float x0, x1;
+        upk2(sub2(pk2(sqrt_approx(a0), sqrt_approx(a1)), pk2(sqrt_approx(c0), sqrt_approx(c1))), x0, x1);
+        x0 = fabsf(x0);
+        x1 = fabsf(x1);
         sure[2 * k] = x0 <= b1;
         dec[2 * k] = sure[2 * k] || (x0 > b2);
         sure[2 * k + 1] = x1 <= b1;
