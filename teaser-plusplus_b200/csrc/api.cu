@@ -1074,7 +1074,8 @@ int tzr_compute_fpfh(tzr_ctx* ctx, const float* pts, int n, double normal_search
   const size_t pb = (size_t)n * 12, nb = (size_t)n * 16, hb = (size_t)n * 33 * 4;
   int rc;
   if ((rc = ensure(ctx, ctx->m_in, al(pb))) != TZR_OK) return rc;
-  if ((rc = ensure(ctx, ctx->m_scratch, al(nb) + al(hb) + 256)) != TZR_OK) return rc;
+  const size_t gb = fpfh_grid_scratch_bytes(n);
+  if ((rc = ensure(ctx, ctx->m_scratch, al(nb) + al(hb) + 256 + gb)) != TZR_OK) return rc;
   if ((rc = ensure(ctx, ctx->m_out, al(hb))) != TZR_OK) return rc;
   float* d_pts = (float*)ctx->m_in.p;
   float4* d_normals = (float4*)ctx->m_scratch.p;
@@ -1082,8 +1083,9 @@ int tzr_compute_fpfh(tzr_ctx* ctx, const float* pts, int n, double normal_search
   int* d_overflow = (int*)((char*)ctx->m_scratch.p + al(nb) + al(hb));
   float* d_out = (float*)ctx->m_out.p;
   CK(cudaMemcpyAsync(d_pts, pts, pb, cudaMemcpyHostToDevice, st));
+  void* d_grid = gb ? (void*)((char*)ctx->m_scratch.p + al(nb) + al(hb) + 256) : nullptr;
   ctx->launches += launch_fpfh(d_pts, n, normal_search_radius, fpfh_search_radius, d_normals, d_spfh, d_out,
-                               d_overflow, st);
+                               d_overflow, d_grid, st);
   if ((rc = check_launch(ctx, "fpfh launch")) != TZR_OK) return rc;
   int overflow = 0;
   CK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -15,10 +15,18 @@
 //
 // Elementary functions: the det_* routines below are operation-for-operation copies of oracle/fpfh_oracle.cc's
 // (IEEE float + - * / sqrt only, -fmad=false), so the device output is comparable bit for bit with the restatement.
-// Brute force is deliberate for now: descriptors are computed on voxel-downsampled clouds (10^3..10^5 points), where
-// n^2 float distance tests from L2-resident points cost milliseconds; a uniform-grid search is the next step if
-// clouds grow.
+// Radius search: brute force below kGridMinN points (n^2 float distance tests from L2-resident points cost well under a
+// millisecond there); above, a hashed uniform grid with cell edge = the larger radius * (1 + 1e-5): points are sorted
+// by bucket (CUB radix sort — library call, like the matcher's), every query visits the <= 27 distinct buckets of its
+// 3x3x3 cell neighbourhood and applies the SAME float distance test, so the neighbour sets — and everything downstream —
+// are identical to the brute-force ones (a point two cells away is farther than the radius by more than the float
+// error of the test; hash collisions only add candidates that fail it).
 #include <math_constants.h>
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstring>
 
 #include "tzr_internal.cuh"
 
@@ -205,14 +213,93 @@ __device__ bool pair_features(const float* p1, const float* n1, const float* p2,
   return true;
 }
 
+
+constexpr int kGridMinN = 4096;
+
+struct Grid {          // all-zero (n_sorted == 0) means brute force
+  const int* sorted;   // point indices sorted by bucket
+  const int* bstart;   // [T] first position of every bucket in sorted
+  const int* bend;     // [T] one past the last
+  int n_sorted;
+  unsigned int mask;   // T - 1
+  double ox, oy, oz;   // grid origin (bounding-box minimum)
+  double inv_h;        // 1 / cell edge
+};
+
+__device__ __forceinline__ unsigned int cell_hash(long long ix, long long iy, long long iz, unsigned int mask) {
+  return ((unsigned int)(ix * 73856093ll) ^ (unsigned int)(iy * 19349663ll) ^ (unsigned int)(iz * 83492791ll)) & mask;
+}
+
+__device__ __forceinline__ bool cell_of(const Grid& g, float x, float y, float z, long long* ix, long long* iy,
+                                        long long* iz) {
+  if (!(x == x) || !(y == y) || !(z == z)) return false;
+  const double fx = floor(((double)x - g.ox) * g.inv_h), fy = floor(((double)y - g.oy) * g.inv_h),
+               fz = floor(((double)z - g.oz) * g.inv_h);
+  if (!(fabs(fx) < 4e18) || !(fabs(fy) < 4e18) || !(fabs(fz) < 4e18)) return false;  // +-inf coordinates
+  *ix = (long long)fx;
+  *iy = (long long)fy;
+  *iz = (long long)fz;
+  return true;
+}
+
+// bounding-box minimum over finite coordinates (ordered-int encoding of floats)
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void bbox_min_kernel(const float* __restrict__ pts, int n, int* mins /*[3], init INT_MAX*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int m[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+  if (i < n)
+    for (int k = 0; k < 3; ++k) {
+      const float v = pts[3 * (size_t)i + k];
+      if (v == v && fabsf(v) < 3.0e38f) m[k] = f2ord(v);
+    }
+  for (int k = 0; k < 3; ++k) {
+    for (int off = 16; off; off >>= 1) m[k] = min(m[k], __shfl_xor_sync(0xffffffffu, m[k], off));
+    if ((threadIdx.x & 31) == 0 && m[k] != 0x7fffffff) atomicMin(&mins[k], m[k]);
+  }
+}
+
+__global__ void bucket_kernel(const float* __restrict__ pts, int n, const int* __restrict__ mins, double inv_h,
+                              unsigned int mask, unsigned int* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Grid g{};
+  g.ox = (double)ord2f(mins[0]);
+  g.oy = (double)ord2f(mins[1]);
+  g.oz = (double)ord2f(mins[2]);
+  g.inv_h = inv_h;
+  long long ix, iy, iz;
+  const float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+  const bool ok = cell_of(g, x, y, z, &ix, &iy, &iz);
+  keys[i] = ok ? cell_hash(ix, iy, iz, mask) : (mask + 1u);  // non-finite points: a bucket nobody visits
+  idx[i] = i;
+  // a finite point the grid cannot index (extent / radius beyond 2^62 cells): tell the host to use brute force
+  if (!ok && x == x && y == y && z == z && fabsf(x) < 3.0e38f && fabsf(y) < 3.0e38f && fabsf(z) < 3.0e38f)
+    const_cast<int*>(mins)[3] = 1;
+}
+
+__global__ void bucket_bounds_kernel(const unsigned int* __restrict__ keys, int n, unsigned int mask,
+                                     int* __restrict__ bstart, int* __restrict__ bend) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned int k = keys[i];
+  if (k > mask) return;
+  if (i == 0 || keys[i - 1] != k) bstart[k] = i;
+  if (i == n - 1 || keys[i + 1] != k) bend[k] = i + 1;
+}
+
 // Block-wide radius search of point q: keys[] (shared, kNbCap) receives (d2 bits << 32 | index) of every point with
 // d2 < r2, unordered.  Returns the count (may exceed kNbCap: overflow, caller flags it).  Contains __syncthreads.
 __device__ int collect_neighbors(const float* __restrict__ pts, int n, int q, float r2, unsigned long long* keys,
-                                 int* s_count) {
+                                 int* s_count, const Grid& g) {
+  __shared__ int s_rs[28], s_re[28], s_pref[28];
   if (threadIdx.x == 0) *s_count = 0;
-  __syncthreads();
   const float qx = pts[3 * (size_t)q], qy = pts[3 * (size_t)q + 1], qz = pts[3 * (size_t)q + 2];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  auto test = [&](int i) {
     const float dx = qx - pts[3 * (size_t)i], dy = qy - pts[3 * (size_t)i + 1], dz = qz - pts[3 * (size_t)i + 2];
     float d = dx * dx;
     d += dy * dy;
@@ -221,6 +308,46 @@ __device__ int collect_neighbors(const float* __restrict__ pts, int n, int q, fl
       const int pos = atomicAdd(s_count, 1);
       if (pos < kNbCap) keys[pos] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)i;
     }
+  };
+  if (g.n_sorted == 0) {  // brute force
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) test(i);
+    __syncthreads();
+    return *s_count;
+  }
+  // the <= 27 distinct buckets of the 3x3x3 cell neighbourhood
+  if (threadIdx.x < 27) {
+    long long ix, iy, iz;
+    int rs = 0, re = 0;
+    if (cell_of(g, qx, qy, qz, &ix, &iy, &iz)) {
+      const int t = threadIdx.x;
+      const unsigned int b = cell_hash(ix + (t % 3) - 1, iy + ((t / 3) % 3) - 1, iz + (t / 9) - 1, g.mask);
+      bool dup = false;
+      for (int u = 0; u < t; ++u)
+        dup |= cell_hash(ix + (u % 3) - 1, iy + ((u / 3) % 3) - 1, iz + (u / 9) - 1, g.mask) == b;
+      if (!dup) {
+        rs = g.bstart[b];
+        re = g.bend[b];
+      }
+    }
+    s_rs[threadIdx.x] = rs;
+    s_re[threadIdx.x] = re;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int t = 0; t < 27; ++t) {
+      s_pref[t] = acc;
+      acc += s_re[t] - s_rs[t];
+    }
+    s_pref[27] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[27];
+  for (int c = threadIdx.x; c < total; c += blockDim.x) {
+    int t = 0;
+    while (c >= s_pref[t + 1]) ++t;
+    test(g.sorted[s_rs[t] + (c - s_pref[t])]);
   }
   __syncthreads();
   return *s_count;
@@ -250,11 +377,12 @@ __device__ void sort_keys(unsigned long long* keys, int count) {
 }
 
 __global__ void __launch_bounds__(kFpfhThreads) normals_kernel(const float* __restrict__ pts, int n, float r2,
-                                                              float4* __restrict__ normals, int* overflow) {
+                                                              float4* __restrict__ normals, int* overflow,
+                                                              Grid g) {
   __shared__ unsigned long long keys[kNbCap];
   __shared__ int s_count;
   const int p = blockIdx.x;
-  const int cnt = collect_neighbors(pts, n, p, r2, keys, &s_count);
+  const int cnt = collect_neighbors(pts, n, p, r2, keys, &s_count, g);
   if (cnt > kNbCap) {
     if (threadIdx.x == 0) {
       atomicExch(overflow, 1);
@@ -318,13 +446,13 @@ __device__ __forceinline__ int bin11(double v) {  // static_cast<int>(floor(v)) 
 
 __global__ void __launch_bounds__(kFpfhThreads) spfh_kernel(const float* __restrict__ pts,
                                                            const float4* __restrict__ normals, int n, float r2,
-                                                           float* __restrict__ spfh, int* overflow) {
+                                                           float* __restrict__ spfh, int* overflow, Grid g) {
   __shared__ unsigned long long keys[kNbCap];
   __shared__ int s_count;
   __shared__ int s_bins[33];
   const int p = blockIdx.x;
   if (threadIdx.x < 33) s_bins[threadIdx.x] = 0;
-  const int cnt = collect_neighbors(pts, n, p, r2, keys, &s_count);  // its barriers also publish s_bins
+  const int cnt = collect_neighbors(pts, n, p, r2, keys, &s_count, g);  // its barriers also publish s_bins
   if (cnt > kNbCap) {
     if (threadIdx.x == 0) atomicExch(overflow, 1);
     if (threadIdx.x < 33) spfh[(size_t)p * 33 + threadIdx.x] = 0.f;
@@ -357,11 +485,11 @@ __global__ void __launch_bounds__(kFpfhThreads) spfh_kernel(const float* __restr
 
 __global__ void __launch_bounds__(kFpfhThreads) fpfh_kernel(const float* __restrict__ pts,
                                                            const float* __restrict__ spfh, int n, float r2,
-                                                           float* __restrict__ out, int* overflow) {
+                                                           float* __restrict__ out, int* overflow, Grid g) {
   __shared__ unsigned long long keys[kNbCap];
   __shared__ int s_count;
   const int p = blockIdx.x;
-  const int cnt = collect_neighbors(pts, n, p, r2, keys, &s_count);
+  const int cnt = collect_neighbors(pts, n, p, r2, keys, &s_count, g);
   if (cnt > kNbCap) {
     if (threadIdx.x == 0) atomicExch(overflow, 1);
     if (threadIdx.x < 33) out[(size_t)p * 33 + threadIdx.x] = 0.f;
@@ -395,16 +523,74 @@ __global__ void __launch_bounds__(kFpfhThreads) fpfh_kernel(const float* __restr
 
 }  // namespace
 
-// pts, normals (n float4), spfh (n x 33), out (n x 33), overflow (int, zeroed here): device pointers.
+size_t fpfh_grid_scratch_bytes(int n) {
+  if (n < kGridMinN) return 0;
+  unsigned int T = 1024;
+  while (T < 2u * (unsigned int)n) T <<= 1;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, n);
+  return 4 * (size_t)n * 4 + 2 * (size_t)T * 4 + 64 + cub_bytes + 1024;
+}
+
+// pts, normals (n float4), spfh (n x 33), out (n x 33), overflow (int, zeroed here), grid_scratch
+// (fpfh_grid_scratch_bytes(n) bytes, may be null below kGridMinN): device pointers.
 int launch_fpfh(const float* pts, int n, double normal_radius, double fpfh_radius, float4* normals, float* spfh,
-                float* out, int* overflow, cudaStream_t st) {
+                float* out, int* overflow, void* grid_scratch, cudaStream_t st) {
   const float r2n = (float)(normal_radius * normal_radius);
   const float r2f = (float)(fpfh_radius * fpfh_radius);
+  int nl = 0;
   cudaMemsetAsync(overflow, 0, sizeof(int), st);
-  normals_kernel<<<n, kFpfhThreads, 0, st>>>(pts, n, r2n, normals, overflow);
-  spfh_kernel<<<n, kFpfhThreads, 0, st>>>(pts, normals, n, r2f, spfh, overflow);
-  fpfh_kernel<<<n, kFpfhThreads, 0, st>>>(pts, spfh, n, r2f, out, overflow);
-  return 3;
+  Grid g{};
+  if (n >= kGridMinN && grid_scratch) {
+    unsigned int T = 1024;
+    while (T < 2u * (unsigned int)n) T <<= 1;
+    char* w = (char*)grid_scratch;
+    unsigned int* keys = (unsigned int*)w;  w += (size_t)n * 4;
+    unsigned int* keys2 = (unsigned int*)w; w += (size_t)n * 4;
+    int* idx = (int*)w;                     w += (size_t)n * 4;
+    int* idx2 = (int*)w;                    w += (size_t)n * 4;
+    int* bstart = (int*)w;                  w += (size_t)T * 4;
+    int* bend = (int*)w;                    w += (size_t)T * 4;
+    int* mins = (int*)w;                    w += 64;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                    (const int*)nullptr, (int*)nullptr, n);
+    const double h = std::max(normal_radius, fpfh_radius) * (1.0 + 1e-5);
+    int bits = 1;
+    while ((1u << bits) <= T) ++bits;  // keys go up to T (the sentinel bucket)
+    const int init[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0};
+    cudaMemcpyAsync(mins, init, 16, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(bstart, 0, 2 * (size_t)T * 4, st);
+    bbox_min_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, mins);
+    bucket_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, mins, 1.0 / h, T - 1, keys, idx);
+    cub::DeviceRadixSort::SortPairs((void*)w, cub_bytes, keys, keys2, idx, idx2, n, 0, bits, st);
+    bucket_bounds_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys2, n, T - 1, bstart, bend);
+    nl += 4;
+    // the Grid travels by value, so the origin has to be known on the host: one 12-byte read-back
+    int hm[4];
+    cudaMemcpyAsync(hm, mins, 16, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    auto dec = [](int i) {
+      const int b = i >= 0 ? i : i ^ 0x7fffffff;
+      float f;
+      memcpy(&f, &b, 4);
+      return (double)f;
+    };
+    g.sorted = idx2;
+    g.bstart = bstart;
+    g.bend = bend;
+    g.n_sorted = hm[3] ? 0 : n;  // 0 = brute force
+    g.mask = T - 1;
+    g.ox = dec(hm[0]);
+    g.oy = dec(hm[1]);
+    g.oz = dec(hm[2]);
+    g.inv_h = 1.0 / h;
+  }
+  normals_kernel<<<n, kFpfhThreads, 0, st>>>(pts, n, r2n, normals, overflow, g);
+  spfh_kernel<<<n, kFpfhThreads, 0, st>>>(pts, normals, n, r2f, spfh, overflow, g);
+  fpfh_kernel<<<n, kFpfhThreads, 0, st>>>(pts, spfh, n, r2f, out, overflow, g);
+  return nl + 3;
 }
 
 }  // namespace tzr

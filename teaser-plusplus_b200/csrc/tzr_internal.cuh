@@ -128,8 +128,9 @@ void launch_scalar_tls(const double* x, const double* ranges, long long m, doubl
                        double* out_est, uint8_t* inliers, cudaStream_t st);
 
 // fpfh.cu (FPFHEstimation::computeFPFHFeatures, fpfh.cc:15-43)
+size_t fpfh_grid_scratch_bytes(int n);
 int launch_fpfh(const float* pts, int n, double normal_radius, double fpfh_radius, float4* normals, float* spfh,
-                float* out, int* overflow, cudaStream_t st);
+                float* out, int* overflow, void* grid_scratch, cudaStream_t st);
 
 // certify.cu (DRSCertifier::certify, certification.cc:40-190); mode 0 certify, 1 initial matrix, 2 dual projection
 int certify_device(int mode, double noise_bound, double cbar2, double sub_optimality, double max_iterations,

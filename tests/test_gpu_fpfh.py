@@ -48,6 +48,26 @@ def test_random_surface_bit_exact(ctx, n, rn, rf, seed):
     assert _same(got, want)
 
 
+@pytest.mark.parametrize("n,rn,rf,seed", [(4096, 0.06, 0.09, 11), (20000, 0.02, 0.03, 12), (9000, 0.5, 0.7, 13)])
+def test_grid_search_path_bit_exact(ctx, n, rn, rf, seed):
+    """n >= 4096 takes the hashed-grid radius search: same neighbour sets, so still bit-exact vs the brute-force
+    restatement — including a cloud with NaN / inf / far-away points and a radius comparable to the extent."""
+    rng = np.random.default_rng(seed)
+    uv = rng.uniform(-1, 1, size=(n, 2))
+    pts = np.stack([uv[:, 0], uv[:, 1], 0.3 * np.sin(3 * uv[:, 0]) * np.cos(2 * uv[:, 1])], axis=1)
+    pts = (pts + rng.normal(scale=0.003, size=pts.shape) + np.array([-0.5, 0.2, 2.0])).astype(np.float32)
+    if seed == 13:
+        pts = pts[:, [2, 0, 1]].copy()
+        pts[:2000] *= np.float32(0.3)       # dense core: up to a few thousand neighbours, fewer than the 4096 cap
+    pts[17] = [np.nan, 0, 0]
+    pts[18] = [np.inf, 0, 0]
+    pts[19] = [1e6, -1e6, 1e6]
+    got, nrm = ctx.compute_fpfh(pts, rn, rf, return_normals=True)
+    want, wn = orc.compute_fpfh(pts, rn, rf)
+    assert _same(nrm, wn)
+    assert _same(got, want)
+
+
 def test_duplicates_isolated_points_and_nan_inputs(ctx):
     rng = np.random.default_rng(9)
     pts = rng.uniform(0, 1, size=(600, 3)).astype(np.float32)

@@ -765,3 +765,20 @@ def test_maximum_size_problem(ctx):
     with pytest.raises(capi.TzrError):
         big = np.zeros((n + 1, 3))
         ctx.solve(big, big, p)
+
+
+@pytest.mark.parametrize("ratio,n", [(0.0, 2000), (0.5, 2500), (0.999, 3000)])
+def test_outlier_ratio_extremes_vs_oracle(ctx, ratio, n):
+    """All-inlier input (complete graph, clique = everything), half outliers, and a 3-inlier needle."""
+    pr = synth.make_problem(n, ratio, seed=int(ratio * 1000) + n, model="ball", sigma=0.01,
+                            noise_bound=synth.NOISE_BOUND_SIGMA_001)
+    kw = fixed_params(pr["noise_bound"])
+    out = ctx.solve(pr["src"], pr["dst"], capi.default_params(**kw))
+    o = orc.solve(pr["src"], pr["dst"], orc.default_params(**kw))
+    assert out["valid"] == o["valid"]
+    assert np.array_equal(out["clique"], o["clique"])
+    assert out["n_edges"] == int(o["sol"].n_edges)
+    if ratio < 0.9:
+        assert set(pr["inliers"].tolist()) <= set(out["clique"].tolist())
+    assert synth.angular_error(out["R"], o["R"]) < ROT_TOL
+    assert np.linalg.norm(out["t"] - o["t"]) < TRANS_TOL
