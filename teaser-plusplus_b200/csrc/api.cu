@@ -44,6 +44,7 @@ struct tzr_ctx {
   cudaStream_t gstream = nullptr, hstream = nullptr;
   cudaEvent_t join_ev = nullptr, join_ev2 = nullptr;
   std::vector<cudaEvent_t> gdone_ev;
+  void* solver_handle = nullptr;  // cusolverDnHandle_t of the certifier, created on first use (certify.cu)
   cudaStream_t copy_stream = nullptr;  // H2D of chunk k+1 overlaps the kernels of chunk k (host-pointer batches)
   std::vector<cudaEvent_t> chunk_ev;
 };
@@ -538,6 +539,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   for (cudaEvent_t e : ctx->stage_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->graph_ev) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  certify_release(ctx->solver_handle);
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
@@ -1037,7 +1039,7 @@ int tzr_certify(tzr_ctx* ctx, const tzr_certifier_params* params, const double* 
   const int rc = certify_device(0, params->noise_bound, params->cbar2, params->sub_optimality, params->max_iterations,
                                 params->gamma_tau, R_colmajor9, src_3xN, dst_3xN, theta, n, &opt, &best, &iters, traj,
                                 traj_capacity, nullptr, nullptr, nullptr, nullptr, &ctx->cert.p, &ctx->cert.cap,
-                                &ctx->launches, ctx->stream, &ctx->last_error);
+                                &ctx->solver_handle, &ctx->launches, ctx->stream, &ctx->last_error);
   if (rc != TZR_OK) return rc;
   result->is_optimal = opt;
   result->n_iterations = iters;
@@ -1053,14 +1055,14 @@ int tzr_certifier_initial_matrix(tzr_ctx* ctx, const tzr_certifier_params* param
   cudaSetDevice(ctx->device);
   return certify_device(1, params->noise_bound, params->cbar2, 0, 0, 0, R_colmajor9, src_3xN, dst_3xN, theta, n,
                         nullptr, nullptr, nullptr, nullptr, 0, M_init, mu, nullptr, nullptr, &ctx->cert.p,
-                        &ctx->cert.cap, &ctx->launches, ctx->stream, &ctx->last_error);
+                        &ctx->cert.cap, &ctx->solver_handle, &ctx->launches, ctx->stream, &ctx->last_error);
 }
 
 int tzr_certifier_dual_projection(tzr_ctx* ctx, const double* W, const double* theta, int n, double* W_dual) {
   if (!ctx || !W || !theta || !W_dual || n <= 0) return TZR_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   return certify_device(2, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr, theta, n, nullptr, nullptr, nullptr, nullptr, 0,
-                        nullptr, nullptr, W, W_dual, &ctx->cert.p, &ctx->cert.cap, &ctx->launches, ctx->stream,
+                        nullptr, nullptr, W, W_dual, &ctx->cert.p, &ctx->cert.cap, &ctx->solver_handle, &ctx->launches, ctx->stream,
                         &ctx->last_error);
 }
 

@@ -489,38 +489,29 @@ static int launch_dual_projection(const CertWork& w, int N, cudaStream_t st) {
   return 5;
 }
 
-struct CertDriver {
-  cusolverDnHandle_t handle = nullptr;
-};
-
-static CertDriver& driver() {
-  static CertDriver d;
-  return d;
-}
-
 // Returns TZR_OK or a negative status; err receives a message.  All pointers host.  mode: 0 full certify,
 // 1 initial matrix only (M_init_out n*n, mu_out), 2 dual projection only (W_in n*n -> Wd_out n*n; theta = N values).
 int certify_device(int mode, double noise_bound, double cbar2, double sub_optimality, double max_iterations,
                    double gamma_tau, const double* R_cm, const double* src, const double* dst, const double* theta,
                    int N, int* is_optimal, double* best_subopt, int* n_iters, double* traj, int traj_cap,
                    double* M_init_out, double* mu_out, const double* W_in, double* Wd_out, void** scratch,
-                   size_t* scratch_cap, int64_t* launches, cudaStream_t st, std::string* err) {
+                   size_t* scratch_cap, void** solver_handle, int64_t* launches, cudaStream_t st, std::string* err) {
   const size_t n = 4 * (size_t)N + 4, nn = n * n;
   if (n > 32768) return TZR_ERR_TOO_LARGE;
   int lwork = 0;
   Cusolver& cs = cusolver();
-  CertDriver& drv = driver();
+  cusolverDnHandle_t& handle = *reinterpret_cast<cusolverDnHandle_t*>(solver_handle);  // owned by the context
   if (mode == 0) {
     if (!cs.ok) {
       *err = cs.err;
       return TZR_ERR_UNSUPPORTED;
     }
-    if (!drv.handle && cs.create(&drv.handle) != CUSOLVER_STATUS_SUCCESS) {
+    if (!handle && cs.create(&handle) != CUSOLVER_STATUS_SUCCESS) {
       *err = "cusolverDnCreate failed";
       return TZR_ERR_CUDA;
     }
-    cs.set_stream(drv.handle, st);
-    if (cs.syevd_buf(drv.handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n, nullptr,
+    cs.set_stream(handle, st);
+    if (cs.syevd_buf(handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n, nullptr,
                      &lwork) != CUSOLVER_STATUS_SUCCESS) {
       *err = "cusolverDnDsyevd_bufferSize failed";
       return TZR_ERR_CUDA;
@@ -609,7 +600,7 @@ int certify_device(int mode, double noise_bound, double cbar2, double sub_optima
   for (size_t iter = 0; (double)iter < max_iterations; ++iter) {
     // nearest PSD matrix (linalg.h:84-99)
     sym_kernel<<<ge, 256, 0, st>>>(w.M, (int)n, w.B);
-    if (cs.syevd(drv.handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, w.B, (int)n, w.w, w.work,
+    if (cs.syevd(handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, w.B, (int)n, w.w, w.work,
                  lwork, w.info) != CUSOLVER_STATUS_SUCCESS) {
       *err = "cusolverDnDsyevd failed";
       return TZR_ERR_CUDA;
@@ -623,7 +614,7 @@ int certify_device(int mode, double noise_bound, double cbar2, double sub_optima
     affine_out_kernel<<<ge, 256, 0, st>>>(w.M_init, w.Wd, (long long)nn, w.M_aff);
     // sub-optimality gap (:192-231): smallest eigenvalue of sym(M_affine)
     sym_kernel<<<ge, 256, 0, st>>>(w.M_aff, (int)n, w.B);
-    if (cs.syevd(drv.handle, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, w.B, (int)n, w.w, w.work,
+    if (cs.syevd(handle, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, w.B, (int)n, w.w, w.work,
                  lwork, w.info) != CUSOLVER_STATUS_SUCCESS) {
       *err = "cusolverDnDsyevd (values) failed";
       return TZR_ERR_CUDA;
@@ -653,6 +644,10 @@ int certify_device(int mode, double noise_bound, double cbar2, double sub_optima
   *n_iters = iters;
   if (cudaStreamSynchronize(st) != cudaSuccess) return TZR_ERR_CUDA;
   return TZR_OK;
+}
+
+void certify_release(void* solver_handle) {
+  if (solver_handle && cusolver().ok) cusolver().destroy((cusolverDnHandle_t)solver_handle);
 }
 
 }  // namespace tzr

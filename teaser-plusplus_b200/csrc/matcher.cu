@@ -320,11 +320,8 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 int launch_feature_nn(const float* query, int nq, const float* db, int ndb, int dim, unsigned long long* best,
                       int num_sms, cudaStream_t st) {
   const size_t smem = (size_t)2 * dim * kNnTile * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (smem > 48 * 1024)  // per device and cheap: no process-wide "already set" flag (one context per GPU is allowed)
     cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMatchMaxDim * kNnTile * 4);
-    attr_set = true;
-  }
   fill_u64_kernel<<<std::min(1024, (nq + 255) / 256), 256, 0, st>>>(best, nq, ~0ull);
   const int qt = (nq + kNnTile - 1) / kNnTile;
   const int db_tiles = (ndb + kNnTile - 1) / kNnTile;

@@ -137,7 +137,8 @@ int certify_device(int mode, double noise_bound, double cbar2, double sub_optima
                    double gamma_tau, const double* R_cm, const double* src, const double* dst, const double* theta,
                    int N, int* is_optimal, double* best_subopt, int* n_iters, double* traj, int traj_cap,
                    double* M_init_out, double* mu_out, const double* W_in, double* Wd_out, void** scratch,
-                   size_t* scratch_cap, int64_t* launches, cudaStream_t st, std::string* err);
+                   size_t* scratch_cap, void** solver_handle, int64_t* launches, cudaStream_t st, std::string* err);
+void certify_release(void* solver_handle);
 
 // matcher.cu (Matcher::calculateCorrespondences, matcher.cc:21-337)
 int launch_feature_nn(const float* query, int nq, const float* db, int ndb, int dim, unsigned long long* best,
