@@ -940,10 +940,39 @@ int tzr_solve_batch(tzr_ctx* ctx, const tzr_params* params, int B, const int32_t
   for (int b = 1; b < B; ++b) uniform &= (n[b] == n[0]);
   if (cliques && max_n < *std::max_element(n, n + B)) return TZR_ERR_INVALID_ARG;
   if (uniform) return solve_uniform_host(ctx, params, B, n[0], src, dst, solutions, cliques, max_n, nullptr, nullptr);
-  for (int b = 0; b < B; ++b) {
-    int rc = solve_uniform_host(ctx, params, 1, n[b], src + b, dst + b, solutions + b,
-                                cliques ? cliques + (size_t)b * max_n : nullptr, max_n, nullptr, nullptr);
+  // ragged batch: problems of equal size are solved together (one device batch per distinct n, largest first)
+  std::vector<int> order(B);
+  for (int b = 0; b < B; ++b) order[b] = b;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return n[a] > n[c]; });
+  std::vector<const double*> gs, gd;
+  std::vector<tzr_solution> gsol;
+  std::vector<int32_t> gclq;
+  for (int lo = 0; lo < B;) {
+    int hi = lo;
+    while (hi < B && n[order[hi]] == n[order[lo]]) ++hi;
+    const int G = hi - lo, ng = n[order[lo]];
+    if (ng <= 0) return TZR_ERR_INVALID_ARG;
+    gs.resize(G);
+    gd.resize(G);
+    gsol.resize(G);
+    for (int g = 0; g < G; ++g) {
+      gs[g] = src[order[lo + g]];
+      gd[g] = dst[order[lo + g]];
+      if (!gs[g] || !gd[g]) return TZR_ERR_INVALID_ARG;
+    }
+    if (cliques) gclq.resize((size_t)G * ng);
+    int rc = solve_uniform_host(ctx, params, G, ng, gs.data(), gd.data(), gsol.data(), cliques ? gclq.data() : nullptr,
+                                ng, nullptr, nullptr);
     if (rc) return rc;
+    for (int g = 0; g < G; ++g) {
+      const int b = order[lo + g];
+      solutions[b] = gsol[g];
+      if (cliques) {
+        const int m = std::max(0, std::min(ng, gsol[g].clique_size));
+        memcpy(cliques + (size_t)b * max_n, gclq.data() + (size_t)g * ng, (size_t)m * sizeof(int32_t));
+      }
+    }
+    lo = hi;
   }
   return TZR_OK;
 }

@@ -385,6 +385,20 @@ def test_solve_batch_ragged(ctx):
         assert synth.angular_error(o["R"], capi.rotation_from_solution_record(sols[b])) <= ROT_TOL
 
 
+def test_solve_batch_ragged_groups_by_size(ctx):
+    """Mixed sizes with repeats: problems of equal n travel as one device batch, results return in caller order."""
+    sizes = [300, 150, 300, 64, 150, 300, 2, 150]
+    prs = [synth.config_problem("C2", b, n=n) for b, n in enumerate(sizes)]
+    p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
+    sols, cliques = ctx.solve_batch([q["src"] for q in prs], [q["dst"] for q in prs], p)
+    for b, q in enumerate(prs):
+        one = ctx.solve(q["src"], q["dst"], p)
+        assert bool(sols[b]["valid"]) == one["valid"]
+        assert np.array_equal(cliques[b], one["clique"])
+        if one["valid"]:
+            assert np.allclose(capi.rotation_from_solution_record(sols[b]), one["R"], atol=1e-12)
+
+
 def test_solve_full_size_c2(ctx):
     pr = synth.config_problem("C2", 0)
     kw = fixed_params(pr["noise_bound"])
