@@ -299,10 +299,19 @@ def main():
         g_ms = float(np.mean(graph_ms))
         achieved = bytes_graph(N_C2) * B / (g_ms * 1e-3) / 1e9
         traffic = None
+        issue = None
         try:
             # measured once with `ncu --set full` (profiles/graph_kernel_traffic.json), scaled to this launch's batch
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "graph_kernel_traffic.json"))).get(
-                "dram_bytes_per_problem") * B
+            prof = json.load(open(os.path.join(ROOT, "profiles", "graph_kernel_traffic.json")))
+            traffic = prof.get("dram_bytes_per_problem") * B
+            # the binding resource of this kernel is the warp-instruction issue rate, not HBM: warp instructions of one
+            # launch (ncu count per problem x B) / live kernel time, against 4 issue slots per SM per clock
+            winst = prof["inst_executed"] / prof["batch"] * B
+            sm_mhz = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+            issue_peak = 148 * 4 * sm_mhz * 1e6
+            issue = {"achieved_warp_inst_per_s": winst / (g_ms * 1e-3), "peak_warp_inst_per_s": issue_peak,
+                     "frac": winst / (g_ms * 1e-3) / issue_peak,
+                     "warp_inst_per_pair": prof["inst_executed"] / prof["batch"] / (N_C2 * (N_C2 - 1) / 2)}
         except Exception:
             pass
         line = {
@@ -319,13 +328,15 @@ def main():
                               "and re-checks the ambiguous band in exact FP64 (bit-identical bitset)",
             },
             "e2e": {"value": e2e, "unit": "registrations/s", "h2d_bytes_per_step": int(2 * B * N_C2 * 24),
-                    "d2h_bytes_per_step": int(B * capi.SOLUTION_DTYPE.itemsize + B * N_C2 * 4),
+                    # what tzr_solve_batch copies back: the solution records + the used prefix of every clique row
+                    "d2h_bytes_per_step": int(B * capi.SOLUTION_DTYPE.itemsize
+                                              + B * int(hsols["clique_size"].max()) * 4),
                     "ms_per_step": t_e2e_max / K},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "graph_strip2_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": bytes_graph(N_C2) * B, "kernel_ms": g_ms,
+                         "algorithmic_bytes_per_launch": bytes_graph(N_C2) * B, "kernel_ms": g_ms, "issue": issue,
                          "note": "issue-bound FP32 stage (12 FP32 ops as 6 packed FP32x2 instructions + 2 MUFU + 2 FSETP "
                                  "per pair, ~60 op/B): the HBM fraction is reported because SURVEY §8d defines the "
                                  "roofline of this stage against HBM; DRAM traffic is within 0.9x of algorithmic"},
