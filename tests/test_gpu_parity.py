@@ -796,3 +796,22 @@ def test_outlier_ratio_extremes_vs_oracle(ctx, ratio, n):
         assert set(pr["inliers"].tolist()) <= set(out["clique"].tolist())
     assert synth.angular_error(out["R"], o["R"]) < ROT_TOL
     assert np.linalg.norm(out["t"] - o["t"]) < TRANS_TOL
+
+
+def test_python_example_bunny():
+    """host/examples/teaser_python_ply.py: the reference's Python quick-start through the pybind module."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "teaser-plusplus_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host])
+    out = subprocess.run([sys.executable, os.path.join(host, "examples", "teaser_python_ply.py"),
+                          os.path.join(synth.GOLDEN_DIR, "bun_zipper_res3.ply")], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    vals = {l.split(":")[0]: float(l.split(":")[1]) for l in out.stdout.strip().splitlines()}
+    # noise bound 0.05 on a 0.15 m object (the reference example's own numbers): a loose pose, but a large clique;
+    # the dense graph makes the exact search run into the 2 s limit set in the example (measured: 597 vertices,
+    # 0.117 rad, 0.009 m)
+    assert vals["rotation error (rad)"] < 0.2 and vals["translation error (m)"] < 0.03
+    assert vals["clique size"] >= 590
