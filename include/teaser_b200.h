@@ -72,7 +72,10 @@ typedef struct tzr_solution {
   double scale;
   double translation[3];
   double rotation[9];             /* column-major */
-  int32_t clique_proven_optimal;  /* 1: maximum clique proven; 0: heuristic mode or budget hit */
+  int32_t clique_proven_optimal;  /* 1: maximum clique proven by complete enumeration (canonical = lexicographically
+                                   * smallest among ties); 2: maximum SIZE proven through the vertex-cover LP bound /
+                                   * Nemhauser-Trotter reduction after the first 50 ms search pass (dense graphs; a
+                                   * maximum clique, not necessarily the canonical one); 0: heuristic mode or budget hit */
   int32_t gnc_iterations;         /* loop bodies entered by the GNC rotation solver */
   double gnc_cost;                /* getGNCRotationCostAtTermination() */
   int32_t n_rotation_inliers;

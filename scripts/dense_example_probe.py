@@ -16,3 +16,4 @@ for lim in (0.5, 5.0):
         t=time.time(); r=ctx.solve(S,D,p); dt=time.time()-t
         print('limit',lim,'mode',mode,'clique',len(r['clique']),'proven',r['proven'],'time',round(dt,2),'rot err',synth.angular_error(T[:3,:3],r['R']),'t err',np.linalg.norm(T[:3,3]-r['t']), 'stage', [round(x,1) for x in r['stage_ms'][:4]], flush=True)
 print(ctx.debug_counters())
+print("proven flag", int(r["sol"].clique_proven_optimal))

@@ -1010,6 +1010,207 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
 // =================================================================================================
 // host-side launcher
 // =================================================================================================
+
+// =================================================================================================
+// K4: Nemhauser–Trotter bound / reduction for problems whose exact search ran out of its first budget.
+//
+// Dense inlier graphs (noise bound comparable to the object size: the reference's Python example has 99 % density
+// among ~800 surviving vertices) defeat colouring bounds, but their COMPLEMENT H inside the alive set A is sparse, and
+// max clique of G[A] = |A| - min vertex cover of H[A].  The LP relaxation of vertex cover equals half the maximum
+// matching of H's bipartite double cover and is usually tight here (LP 212.5 vs optimum 213 on that example), so:
+//   * maximum matching by augmenting paths, one warp per problem, H rows formed on the fly as ~adj[u] & A;
+//   * if |A| - ceil(matching / 2) <= L the incumbent is optimal: done (flag 4);
+//   * otherwise König's construction gives the half-integral LP optimum; by the Nemhauser–Trotter theorem some maximum
+//     clique avoids every vertex with LP value 1, so those leave A (flag 8) and the second search pass runs on the rest.
+// Either way the returned clique has maximum SIZE; which maximum clique is no longer the canonical (lexicographically
+// smallest) one, reported as clique_proven_optimal = 2.  Problems whose first pass completed are not touched.
+// Scratch: the exact-phase cv slots of the problem (free between the passes): mateL | mateR | parent | queue.
+// =================================================================================================
+__global__ void __launch_bounds__(32) clique_lp_kernel(Batch bt) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  if (!(bt.flags[b] & 2)) return;  // only problems that hit the first-pass deadline
+  const int n = bt.n, W = pitch32(n);
+  __shared__ uint32_t s_vis[1024], s_free[1024], s_lz[1024];  // visited R / free R (then: reached L), W <= 1024
+  __shared__ int s_tail;
+  uint32_t* A = bt.alive + (size_t)b * W;
+  const int L = bt.L[b];
+  int cntA = 0;
+  for (int x = lane; x < W; x += 32) cntA += __popc(A[x]);
+  for (int o = 16; o; o >>= 1) cntA += __shfl_xor_sync(0xffffffffu, cntA, o);
+  if (2 * L < cntA) return;  // far from a clique: the LP bound cannot close such a gap
+  int32_t* base = bt.cv + (size_t)b * bt.exact_ctas * kExactWarps * (size_t)n;
+  int32_t *mateL = base, *mateR = base + n, *parent = base + 2 * (size_t)n, *queue = base + 3 * (size_t)n;
+  for (int v = lane; v < n; v += 32) {
+    mateL[v] = -1;
+    mateR[v] = -1;
+  }
+  for (int x = lane; x < W; x += 32) s_free[x] = A[x];
+  __syncwarp();
+  auto hword = [&](const uint32_t* row, int u, int x) {  // word x of H's row u inside A
+    uint32_t m = ~row[x] & A[x];
+    if (x == (u >> 5)) m &= ~(1u << (u & 31));
+    return m;
+  };
+  int matching = 0;
+  // ---- greedy start
+  for (int x0 = 0; x0 < W; ++x0) {
+    uint32_t aw = A[x0];
+    while (aw) {
+      const int u = x0 * 32 + __ffs(aw) - 1;
+      aw &= aw - 1;
+      const uint32_t* row = adj_row32(bt, b, u);
+      int found = -1;
+      for (int base_x = 0; base_x < W && found < 0; base_x += 32) {
+        const int x = base_x + lane;
+        const uint32_t m = x < W ? (hword(row, u, x) & s_free[x]) : 0u;
+        const unsigned nz = __ballot_sync(0xffffffffu, m != 0u);
+        if (nz) {
+          const int sl = __ffs(nz) - 1;
+          const uint32_t mm = __shfl_sync(0xffffffffu, m, sl);
+          found = (base_x + sl) * 32 + __ffs(mm) - 1;
+        }
+      }
+      if (found >= 0) {
+        if (lane == 0) {
+          mateL[u] = found;
+          mateR[found] = u;
+          s_free[found >> 5] &= ~(1u << (found & 31));
+        }
+        ++matching;
+        __syncwarp();
+      }
+    }
+  }
+  // alternating BFS from the left vertices in queue[0..tail); stops at the first free right vertex when `augment`.
+  // Marks reached right vertices in s_vis and (when !augment) reached left vertices in s_lz.
+  auto bfs = [&](int tail0, bool augment) -> int {
+    if (lane == 0) s_tail = tail0;
+    __syncwarp();
+    int head = 0, found = -1;
+    while (found < 0) {
+      const int tail = s_tail;
+      if (head >= tail) break;
+      const int xq = queue[head++];
+      const uint32_t* row = adj_row32(bt, b, xq);
+      for (int base_x = 0; base_x < W; base_x += 32) {
+        const int x = base_x + lane;
+        uint32_t m = 0u;
+        if (x < W) {
+          m = hword(row, xq, x) & ~s_vis[x];
+          s_vis[x] |= m;
+        }
+        while (m) {
+          const int v = x * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          parent[v] = xq;
+          const int mv = mateR[v];
+          if (mv < 0) {
+            if (augment) found = v;  // lane-local; the lowest lane wins below
+          } else {
+            const int pos = atomicAdd(&s_tail, 1);
+            queue[pos] = mv;
+            if (!augment) atomicOr(&s_lz[mv >> 5], 1u << (mv & 31));
+          }
+        }
+        const unsigned anyf = __ballot_sync(0xffffffffu, found >= 0);
+        if (anyf) {
+          found = __shfl_sync(0xffffffffu, found, __ffs(anyf) - 1);
+          break;
+        }
+        __syncwarp();
+      }
+      __syncwarp();
+    }
+    return found;
+  };
+  // ---- augmenting paths from every free left vertex
+  for (int x0 = 0; x0 < W; ++x0) {
+    uint32_t aw = A[x0];
+    while (aw) {
+      const int u = x0 * 32 + __ffs(aw) - 1;
+      aw &= aw - 1;
+      if (mateL[u] >= 0) continue;
+      for (int x = lane; x < W; x += 32) s_vis[x] = 0u;
+      if (lane == 0) queue[0] = u;
+      __syncwarp();
+      const int f = bfs(1, true);
+      if (f >= 0) {
+        if (lane == 0) {
+          int v = f;
+          while (v >= 0) {
+            const int xl = parent[v];
+            const int nv = mateL[xl];
+            mateL[xl] = v;
+            mateR[v] = xl;
+            v = nv;
+          }
+        }
+        ++matching;
+      }
+      __syncwarp();
+    }
+  }
+  const int ub = cntA - (matching + 1) / 2;
+  if (ub <= L) {  // LP bound closes the gap: the incumbent is a maximum clique
+    if (lane == 0) {
+      bt.flags[b] = 4;
+      bt.alive_cnt[b] = 0;
+    }
+    return;
+  }
+  // ---- König: Z = everything reachable from the free left vertices by alternating paths
+  for (int x = lane; x < W; x += 32) {
+    s_vis[x] = 0u;
+    s_lz[x] = 0u;
+  }
+  __syncwarp();
+  int tail0 = 0;
+  if (lane == 0) {
+    for (int x0 = 0; x0 < W; ++x0) {
+      uint32_t aw = A[x0];
+      while (aw) {
+        const int u = x0 * 32 + __ffs(aw) - 1;
+        aw &= aw - 1;
+        if (mateL[u] < 0) {
+          queue[tail0++] = u;
+          s_lz[u >> 5] |= 1u << (u & 31);
+        }
+      }
+    }
+  }
+  tail0 = __shfl_sync(0xffffffffu, tail0, 0);
+  __syncwarp();
+  bfs(tail0, false);
+  __syncwarp();
+  // cover C = (L \ Z) u (R n Z); LP value 1 <=> u in both halves: u not reached on the left, reached on the right
+  int removed = 0;
+  for (int x = lane; x < W; x += 32) {
+    const uint32_t v1 = A[x] & ~s_lz[x] & s_vis[x];
+    removed += __popc(v1);
+    A[x] &= ~v1;
+  }
+  for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+  if (lane == 0) {
+    bt.alive_cnt[b] = cntA - removed;
+    if (removed) atomicOr(bt.flags + b, 8);
+  }
+}
+
+// Between the two exact passes: problems still open (deadline hit, not closed by the LP bound) get a fresh work counter
+// and clock; everything else is switched off for the second pass.
+__global__ void clique_resume_kernel(Batch bt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bt.B) return;
+  const int f = bt.flags[b];
+  if ((f & 2) && !(f & 4)) {
+    bt.flags[b] = f & 8;
+    bt.root_ctr[b] = 0;
+    bt.t_start[b] = 0ull;
+  } else {
+    bt.alive_cnt[b] = 0;
+  }
+}
+
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches) {
   const int n = bt.n;
   static bool attr_done = false;
@@ -1033,9 +1234,23 @@ void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t 
   clique_peel_kernel<<<bt.B, kPeelThreads, clique_peel_smem(n), st>>>(b2, mode == 0 ? 0 : 1);
   launches += 2;
   if (mode == 0) {
+    // Two passes: a short first one (every instance the canonical enumeration can finish does so here), then the
+    // Nemhauser–Trotter bound / reduction for whatever ran into that deadline, then the rest of the caller's budget.
+    constexpr unsigned long long kFirstPassNs = 50ull * 1000 * 1000;
+    const unsigned long long total = bt.budget_ns;  // 0 = unlimited
     dim3 g3((unsigned)bt.exact_ctas, (unsigned)bt.B);
-    clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(b2);
-    ++launches;
+    Batch p1 = b2;
+    p1.budget_ns = (total == 0ull || total > kFirstPassNs) ? kFirstPassNs : total;
+    clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(p1);
+    clique_lp_kernel<<<bt.B, 32, 0, st>>>(b2);
+    launches += 2;
+    if (total == 0ull || total > kFirstPassNs) {
+      Batch p2 = b2;
+      p2.budget_ns = total ? total - kFirstPassNs : 0ull;
+      clique_resume_kernel<<<(bt.B + 127) / 128, 128, 0, st>>>(b2);
+      clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(p2);
+      launches += 2;
+    }
   }
   if (n_launches) *n_launches += launches;
 }

@@ -481,7 +481,9 @@ __global__ void __launch_bounds__(kRTThreads) rot_trans_kernel(Batch bt, tzr_par
   if (tid == 0) {
     sol->clique_size = m;
     sol->n_edges = (int64_t)(bt.n_edges2[b] / 2ull);
-    sol->clique_proven_optimal = (use_clique && exact_mode && !(bt.flags[b] & 1)) ? 1 : 0;
+    // 1: enumeration complete (canonical tie-break); 2: maximum size proven through the vertex-cover LP bound /
+    // Nemhauser-Trotter reduction after the first search budget (max_clique.cu K4); 0: budget hit, incumbent returned
+    sol->clique_proven_optimal = (use_clique && exact_mode && !(bt.flags[b] & 1)) ? ((bt.flags[b] & 12) ? 2 : 1) : 0;
     sol->valid = 1;
   }
   if (use_clique && m <= 1) {  // registration.cc:643-647
