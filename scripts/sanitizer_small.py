@@ -46,6 +46,13 @@ t, m = ctx.tls_translation(pr["src"][:50], pr["src"][:50] + 1.0, 0.01)
 e, i = ctx.scalar_tls([0.5, 1, 0.6, 0.7, 1.2], [0.9, 0.9, 0.4, 0.5, 0.4])
 r = ctx.rotation_solve(1, pr["src"][:60], pr["src"][:60], 0.01)
 print("stage calls ok", t, e)
+# dense graph: first exact pass hits its 50 ms deadline (always, under the sanitizer), then clique_lp_kernel + second pass
+rng2 = np.random.default_rng(5)
+ds = rng2.uniform(0, 0.15, size=(500, 3))
+dd = ds + (rng2.random((500, 3)) - 0.5) * 0.1
+dd[:150] += 7.0
+g = ctx.solve(ds, dd, capi.default_params(noise_bound=0.05, estimate_scaling=0, max_clique_time_limit=20.0))
+print("dense", len(g["clique"]), int(g["sol"].clique_proven_optimal))
 # upstream / downstream stages
 mp = synth.matcher_problem(300, 260, 90, seed=3)
 for cc in (False, True):
