@@ -701,14 +701,23 @@ struct CliqueSearch {
   double deadline_ms;
   std::atomic<bool> timed_out;
   std::atomic<i64> nodes;
+  double pass_deadline_ms = -1;       // first pass of the two-pass scheme (see find_max_clique); < 0 = none
+  std::atomic<bool> budget_out{false};
+  int strict = 0;  // 1 after a Nemhauser-Trotter reduction: prune whatever cannot BEAT the incumbent (see find_max_clique)
+  int stop_at = 0x7fffffff;  // ... and stop as soon as the incumbent reaches this (the LP upper bound)
 
   // BBMC-style expansion (Tomita / San Segundo): a greedy sequential colouring of P yields, for the
   // vertices that could still beat the incumbent, a branching order and a colour bound.
   // P lives in S.bits[depth][0..W).
   void expand(std::vector<int>& C, CliqueScratch& S, int depth) {
     i64 nd = nodes.fetch_add(1, std::memory_order_relaxed);
-    if ((nd & 0xfff) == 0 && now_ms() > deadline_ms) timed_out.store(true);
-    if (timed_out.load(std::memory_order_relaxed)) return;
+    if ((nd & 0xff) == 0) {
+      const double t = now_ms();
+      if (t > deadline_ms) timed_out.store(true);
+      if (pass_deadline_ms >= 0 && t > pass_deadline_ms) budget_out.store(true);
+    }
+    if (timed_out.load(std::memory_order_relaxed) || budget_out.load(std::memory_order_relaxed)) return;
+    if (best.load(std::memory_order_relaxed) >= stop_at) return;
     uint64_t* P = S.bits[depth].data();
     uint64_t* Q = P + W;
     uint64_t* R = Q + W;
@@ -716,10 +725,59 @@ struct CliqueSearch {
     // tie the incumbent) and the lexicographically smallest sorted index set is kept.  When the maximum
     // clique is unique this is exactly the reference's answer; when it is not, the reference (PMC, multi-
     // threaded) returns an unspecified one of them.
-    int kmin = best.load(std::memory_order_relaxed) - (int)C.size();
-    if (kmin < 1) kmin = 1;
     int pc = 0;
     for (int w = 0; w < W; ++w) pc += __builtin_popcountll(P[w]);
+    // Universal vertices (adjacent to every other candidate) belong to every maximum clique of this subproblem:
+    // they join C without branching (the device kernel does the same in node_reduce).  Without this, dense
+    // subproblems re-branch over interchangeable universal vertices and never finish.
+    struct PopGuard {
+      std::vector<int>& c;
+      size_t n0;
+      ~PopGuard() { c.resize(n0); }
+    } guard{C, C.size()};
+    if (pc >= 32) {
+      int absorbed = 0;
+      for (int w = 0; w < W; ++w) {
+        uint64_t m = P[w];
+        while (m) {
+          const int bpos = __builtin_ctzll(m);
+          m &= m - 1;
+          const int v = w * 64 + bpos;
+          const uint64_t* nv = A->row(v);
+          int d = 0;
+          for (int x = 0; x < W; ++x) d += __builtin_popcountll(P[x] & nv[x]);
+          if (d == pc - 1) {  // P itself is not modified inside this scan, so the test is against the full candidate set
+            C.push_back(v);
+            ++absorbed;
+          }
+        }
+      }
+      if (absorbed) {
+        for (size_t q = guard.n0; q < C.size(); ++q) P[C[q] >> 6] &= ~(1ull << (C[q] & 63));
+        pc -= absorbed;
+        if (pc == 0) {
+          if ((int)C.size() >= best.load(std::memory_order_relaxed)) {
+#pragma omp critical(orc_clique_update)
+            {
+              if ((int)C.size() > best.load()) {
+                best_clique = C;
+                best.store((int)C.size());
+              } else if ((int)C.size() == best.load()) {
+                std::vector<int> a(C.size()), b(best_clique.size());
+                for (size_t q = 0; q < C.size(); ++q) a[q] = orig[C[q]];
+                for (size_t q = 0; q < best_clique.size(); ++q) b[q] = orig[best_clique[q]];
+                std::sort(a.begin(), a.end());
+                std::sort(b.begin(), b.end());
+                if (b.size() != a.size() || a < b) best_clique = C;
+              }
+            }
+          }
+          return;
+        }
+      }
+    }
+    int kmin = best.load(std::memory_order_relaxed) + strict - (int)C.size();
+    if (kmin < 1) kmin = 1;
     std::vector<int>& ord = S.ord[depth];
     if (ord.size() < 2 * (size_t)pc) ord.resize(2 * (size_t)pc);
     std::memcpy(Q, P, sizeof(uint64_t) * W);
@@ -748,7 +806,7 @@ struct CliqueSearch {
     for (int i = cnt - 1; i >= 0; --i) {
       int v = ord[2 * i];
       int col = ord[2 * i + 1];
-      if ((int)C.size() + col < best.load(std::memory_order_relaxed)) return;
+      if ((int)C.size() + col < best.load(std::memory_order_relaxed) + strict) return;
       const uint64_t* nv = A->row(v);
       bool any = false;
       for (int w = 0; w < W; ++w) {
@@ -852,6 +910,7 @@ struct CliqueInfo {
   int exact_ran = 0;
   int timed_out = 0;
   i64 nodes = 0;
+  int lp_closed = 0;  // 1: size proven through the vertex-cover LP bound / Nemhauser-Trotter reduction (not canonical)
 };
 
 // findMaxClique  (teaser/src/graph.cc:12-125)
@@ -902,66 +961,173 @@ std::vector<int> find_max_clique(const std::vector<std::vector<int>>& adj, int m
     int v = order[i];  // ascending core/degeneracy order
     if (core[v] >= lb - 1) keep.push_back(v);
   }
-  const int nk = (int)keep.size();
-  if (nk == 0) return C;
-  std::vector<int> label(n, -1);
-  for (int i = 0; i < nk; ++i) label[keep[i]] = i;
-  Bits A;
-  A.init(nk, nk);
-  for (int i = 0; i < nk; ++i) {
-    int v = keep[i];
-    uint64_t* r = A.row(i);
-    for (i64 e = vertices[v]; e < vertices[v + 1]; ++e) {
-      int l = label[edges[e]];
-      if (l >= 0) r[l >> 6] |= 1ull << (l & 63);
-    }
-  }
-  CliqueSearch S;
-  S.A = &A;
-  S.n = nk;
-  S.W = A.W;
-  S.best.store(lb);
-  S.orig = keep.data();
-  for (int v : C) S.best_clique.push_back(label[v]);  // heuristic clique = first incumbent
-  S.timed_out.store(false);
-  S.nodes.store(0);
-  S.deadline_ms = now_ms() + time_limit_s * 1000.0;
-  const int W = A.W;
-  // roots in reverse degeneracy order; root i only sees later vertices (labels > i)
-#pragma omp parallel num_threads(num_threads)
-  {
-    CliqueScratch scratch;
-    scratch.init(ub + 3, W);
-    std::vector<int> Cc;
-#pragma omp for schedule(dynamic, 1)
-    for (int ri = 0; ri < nk; ++ri) {
-      int i = nk - 1 - ri;
-      if (S.timed_out.load()) continue;
-      // P = N(i) ∩ {j > i}
-      uint64_t* P = scratch.bits[0].data();
-      const uint64_t* r = A.row(i);
-      int pc = 0;
-      for (int w = 0; w < W; ++w) {
-        uint64_t m = r[w];
-        int lo = w * 64;
-        if (lo + 63 <= i) m = 0;
-        else if (lo <= i) m &= ~((2ull << (i - lo)) - 1ull);
-        P[w] = m;
-        pc += __builtin_popcountll(m);
+  if (keep.empty()) return C;
+  const double t_end_ms = now_ms() + time_limit_s * 1000.0;
+  i64 total_nodes = 0;
+  bool timed_out = false;
+  int best = lb;
+  // One search over the vertex list `keep` (compact labels = positions in keep); returns true when it ran to the end.
+  auto run_search = [&](const std::vector<int>& kp, double pass_seconds, int strict = 0, int stop_at = 0x7fffffff) -> bool {
+    const int nk = (int)kp.size();
+    std::vector<int> label(n, -1);
+    for (int i = 0; i < nk; ++i) label[kp[i]] = i;
+    Bits A;
+    A.init(nk, nk);
+    for (int i = 0; i < nk; ++i) {
+      int v = kp[i];
+      uint64_t* r = A.row(i);
+      for (i64 e = vertices[v]; e < vertices[v + 1]; ++e) {
+        int l = label[edges[e]];
+        if (l >= 0) r[l >> 6] |= 1ull << (l & 63);
       }
-      if (pc + 1 < S.best.load()) continue;
-      Cc.clear();
-      Cc.push_back(i);
-      S.expand(Cc, scratch, 0);
     }
-  }
-  if ((int)S.best_clique.size() >= lb) {
-    C.clear();
-    for (int l : S.best_clique) C.push_back(keep[l]);
+    CliqueSearch S;
+    S.A = &A;
+    S.n = nk;
+    S.W = A.W;
+    S.best.store(best);
+    S.orig = kp.data();
+    bool inc_ok = true;
+    for (int v : C) inc_ok &= label[v] >= 0;
+    if (inc_ok)
+      for (int v : C) S.best_clique.push_back(label[v]);  // incumbent = first candidate of the tie-break
+    S.timed_out.store(false);
+    S.nodes.store(0);
+    S.deadline_ms = t_end_ms;
+    S.pass_deadline_ms = pass_seconds >= 0 ? now_ms() + pass_seconds * 1000.0 : -1;
+    S.strict = strict;
+    S.stop_at = stop_at;
+    const int W = A.W;
+    // roots in reverse degeneracy order; root i only sees later vertices (labels > i)
+#pragma omp parallel num_threads(num_threads)
+    {
+      CliqueScratch scratch;
+      scratch.init(ub + 3, W);
+      std::vector<int> Cc;
+#pragma omp for schedule(dynamic, 1)
+      for (int ri = 0; ri < nk; ++ri) {
+        int i = nk - 1 - ri;
+        if (S.timed_out.load() || S.budget_out.load() || S.best.load() >= S.stop_at) continue;
+        // P = N(i) ∩ {j > i}
+        uint64_t* P = scratch.bits[0].data();
+        const uint64_t* r = A.row(i);
+        int pc = 0;
+        for (int w = 0; w < W; ++w) {
+          uint64_t m = r[w];
+          int lo = w * 64;
+          if (lo + 63 <= i) m = 0;
+          else if (lo <= i) m &= ~((2ull << (i - lo)) - 1ull);
+          P[w] = m;
+          pc += __builtin_popcountll(m);
+        }
+        if (pc + 1 < S.best.load() + S.strict) continue;
+        Cc.clear();
+        Cc.push_back(i);
+        S.expand(Cc, scratch, 0);
+      }
+    }
+    if ((int)S.best_clique.size() >= best && !S.best_clique.empty()) {
+      std::vector<int> Cn;
+      for (int l : S.best_clique) Cn.push_back(kp[l]);
+      C = Cn;
+      best = (int)C.size();
+    }
+    total_nodes += S.nodes.load();
+    timed_out = S.timed_out.load();
+    return !S.timed_out.load() && !S.budget_out.load();
+  };
+
+  // Pass 1 with a short wall-clock budget: every instance whose canonical enumeration is feasible finishes here
+  // (the device path uses 50 ms of GPU time for the same purpose).
+  const double kFirstPassSeconds = 3.0;
+  bool done = run_search(keep, std::min(kFirstPassSeconds, time_limit_s));
+  if (!done && !timed_out && 2 * best >= (int)keep.size()) {
+    // Dense graph (the device path does the same in clique_lp_kernel, max_clique.cu K4): max clique of G[A] =
+    // |A| - min vertex cover of the complement H[A]; LP relaxation = half the maximum matching of H's bipartite double
+    // cover; Nemhauser-Trotter: some maximum clique avoids the vertices with LP value 1.
+    const int nk = (int)keep.size();
+    std::vector<int> label(n, -1);
+    for (int i = 0; i < nk; ++i) label[keep[i]] = i;
+    std::vector<std::vector<int>> H(nk);
+    {
+      std::vector<char> nb(nk);
+      for (int i = 0; i < nk; ++i) {
+        std::fill(nb.begin(), nb.end(), 0);
+        for (i64 e = vertices[keep[i]]; e < vertices[keep[i] + 1]; ++e)
+          if (label[edges[e]] >= 0) nb[label[edges[e]]] = 1;
+        for (int j = 0; j < nk; ++j)
+          if (j != i && !nb[j]) H[i].push_back(j);
+      }
+    }
+    std::vector<int> mateL(nk, -1), mateR(nk, -1), parent(nk, -1), queue;
+    std::vector<char> vis(nk, 0);
+    int matching = 0;
+    for (int u = 0; u < nk; ++u)
+      for (int v : H[u])
+        if (mateR[v] < 0) {
+          mateL[u] = v;
+          mateR[v] = u;
+          ++matching;
+          break;
+        }
+    auto bfs = [&](bool augment, std::vector<char>* lz) -> int {
+      size_t head = 0;
+      while (head < queue.size()) {
+        const int x = queue[head++];
+        for (int v : H[x]) {
+          if (vis[v]) continue;
+          vis[v] = 1;
+          parent[v] = x;
+          if (mateR[v] < 0) {
+            if (augment) return v;
+          } else {
+            queue.push_back(mateR[v]);
+            if (lz) (*lz)[mateR[v]] = 1;
+          }
+        }
+      }
+      return -1;
+    };
+    for (int u = 0; u < nk; ++u) {
+      if (mateL[u] >= 0) continue;
+      std::fill(vis.begin(), vis.end(), 0);
+      queue.assign(1, u);
+      int v = bfs(true, nullptr);
+      if (v >= 0) {
+        while (v >= 0) {
+          const int x = parent[v], nv = mateL[x];
+          mateL[x] = v;
+          mateR[v] = x;
+          v = nv;
+        }
+        ++matching;
+      }
+    }
+    if (info) info->lp_closed = 1;
+    if (nk - (matching + 1) / 2 <= best) {
+      done = true;  // the incumbent is a maximum clique
+    } else {
+      std::vector<char> lz(nk, 0);
+      std::fill(vis.begin(), vis.end(), 0);
+      queue.clear();
+      for (int u = 0; u < nk; ++u)
+        if (mateL[u] < 0) {
+          queue.push_back(u);
+          lz[u] = 1;
+        }
+      bfs(false, &lz);
+      std::vector<int> keep2;
+      for (int i = 0; i < nk; ++i)
+        if (!(!lz[i] && vis[i])) keep2.push_back(keep[i]);  // drop LP value 1
+      // ties no longer matter (and are astronomically many on dense graphs); reaching the LP bound ends the search
+      done = run_search(keep2, -1, 1, nk - (matching + 1) / 2);
+    }
+  } else if (!done && !timed_out) {
+    done = run_search(keep, -1);
   }
   if (info) {
-    info->timed_out = S.timed_out.load();
-    info->nodes = S.nodes.load();
+    info->timed_out = timed_out ? 1 : 0;
+    info->nodes = total_nodes;
   }
   return C;
 }
@@ -1202,7 +1368,7 @@ int orc_solve(const orc_params* p, const double* src, const double* dst, int n, 
                                  p->max_clique_num_threads, &ci);
     std::sort(max_clique.begin(), max_clique.end());
     sol->stage_ms[3] = now_ms() - t0;
-    sol->clique_proven_optimal = (mode == MODE_PMC_EXACT && !ci.timed_out) ? 1 : 0;
+    sol->clique_proven_optimal = (mode == MODE_PMC_EXACT && !ci.timed_out) ? (ci.lp_closed ? 2 : 1) : 0;
     if (max_clique.size() <= 1) {  // :643-647
       sol->valid = 0;
       sol->clique_size = (int)max_clique.size();

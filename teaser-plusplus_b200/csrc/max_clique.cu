@@ -714,6 +714,8 @@ struct WarpCtx {
   int32_t* cv;                   // global: current clique
   int32_t* centry;               // global: clique size at entry of level d
   volatile int32_t* Lp;
+  int strict;                    // 1 after a Nemhauser-Trotter reduction: only cliques that BEAT the incumbent matter (the
+                                 // canonical tie-break is already forfeited, and dense graphs have astronomically many ties)
   int xlo;                       // word index of the current root: every candidate set is empty below it
 };
 
@@ -726,7 +728,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
       atomicAdd(c.cnt + 3, 1ull);
       atomicAdd(c.cnt + 4, (unsigned long long)cnt);
     }
-    const int Lc = *c.Lp;
+    const int Lc = *c.Lp + c.strict;
     if (csz + cnt < Lc) return 0;  // cannot even tie the incumbent (ties are enumerated: canonical result)
     if (cnt == 0) return 1;
     const int need = Lc - csz - 1;  // a candidate must have >= need neighbours inside P to reach size Lc
@@ -770,14 +772,14 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     csz += added;
     if (!changed) {
       const int cnt2 = cnt - added;
-      const int Lc2 = *c.Lp;
+      const int Lc2 = *c.Lp + c.strict;
       if (csz + cnt2 < Lc2) return 0;
       if (cnt2 == 0) return 1;
       return 2;
     }
   }
   const int cnt = warp_popc(c.Pc, W, lane);
-  if (csz + cnt < *c.Lp) return 0;
+  if (csz + cnt < *c.Lp + c.strict) return 0;
   if (cnt == 0) return 1;
   return 2;
 }
@@ -785,7 +787,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
 // Greedy sequential colouring of Pc; Bs = vertices whose colour >= kmin.  Returns |Bs|.
 __device__ int node_colour(WarpCtx& c, int csz) {
   const int W = c.W, lane = c.lane;
-  int kmin = *c.Lp - csz;  // colour k bounds cliques by k: need csz + k >= L to tie or beat
+  int kmin = *c.Lp + c.strict - csz;  // colour k bounds cliques by k: need csz + k >= L to tie or beat
   if (kmin < 1) kmin = 1;
   for (int x = lane; x < W; x += 32) {
     c.Q[x] = c.Pc[x];
@@ -906,6 +908,8 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
   c.cv = bt.cv + gw * (size_t)n;
   c.centry = bt.centry + gw * (size_t)bt.max_depth;
   c.Lp = bt.L + b;
+  c.strict = (bt.flags[b] & 8) ? 1 : 0;
+  const int ub_stop = c.strict ? (bt.flags[b] >> 8) : 0x7fffffff;  // LP bound of the NT step: reaching it ends the search
   const uint32_t* alive = bt.alive + (size_t)b * W;
   // Params::max_clique_time_limit (graph.cc:44): budget counted from the first search warp of this problem
   unsigned long long deadline = 0ull;
@@ -927,6 +931,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
     if (v >= n) break;
     if (!((alive[v >> 5] >> (v & 31)) & 1u)) continue;
     if (bt.flags[b] & 2) break;  // deadline hit elsewhere
+    if (*c.Lp >= ub_stop) break;
     // root node: P = N(v) ∩ alive ∩ {u > v}
     {
       const uint32_t* rv = adj_row32(bt, b, v);
@@ -953,10 +958,14 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
           depth = 0;
           break;
         }
+        if (*c.Lp >= ub_stop) {
+          depth = 0;
+          break;
+        }
         if (c.cnt && lane == 0) atomicAdd(c.cnt + 2, 1ull);
         const int r = node_reduce(c, csz);
         if (r == 1) {
-          if (csz >= *c.Lp) record_clique(c, csz);
+          if (csz >= *c.Lp + c.strict) record_clique(c, csz);
         } else if (r == 2) {
           const int nB = node_colour(c, csz);
           if (nB > 0) {
@@ -986,7 +995,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
       // cheap level bound: every remaining clique of this level has size <= ce + |P_d| (ties still explored)
       const int cntP = warp_popc(Pd, W, lane);
       int u = -1;
-      if (ce + cntP >= *c.Lp) u = warp_first_bit(Bd, W, lane, 0, &xf);
+      if (ce + cntP >= *c.Lp + c.strict) u = warp_first_bit(Bd, W, lane, 0, &xf);
       if (u < 0) {
         --depth;
         continue;
@@ -1192,7 +1201,8 @@ __global__ void __launch_bounds__(32) clique_lp_kernel(Batch bt) {
   for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
   if (lane == 0) {
     bt.alive_cnt[b] = cntA - removed;
-    if (removed) atomicOr(bt.flags + b, 8);
+    // flag 8: second pass in "beat the incumbent" mode, stopping as soon as it reaches the LP bound kept in bits 8..
+    bt.flags[b] = (bt.flags[b] & 3) | 8 | (ub << 8);
   }
 }
 
@@ -1203,7 +1213,7 @@ __global__ void clique_resume_kernel(Batch bt) {
   if (b >= bt.B) return;
   const int f = bt.flags[b];
   if ((f & 2) && !(f & 4)) {
-    bt.flags[b] = f & 8;
+    bt.flags[b] = f & ~3;
     bt.root_ctr[b] = 0;
     bt.t_start[b] = 0ull;
   } else {

@@ -855,3 +855,7 @@ def test_dense_graph_is_closed_by_the_vertex_cover_bound(ctx):
     assert sub.sum() == len(c) * (len(c) - 1)          # a clique indeed
     obits, _, _ = orc.build_graph_bits(S, D, 0.05)
     assert np.array_equal(bits, obits)                  # on the same graph as the restatement's
+    # the restatement takes the same two-pass route (3 s first pass, LP bound, NT reduction, beat-only second pass)
+    o = orc.solve(S, D, orc.default_params(noise_bound=0.05, cbar2=1.0, estimate_scaling=0,
+                                           rotation_cost_threshold=1e-12, max_clique_time_limit=600.0))
+    assert len(o["clique"]) == 597 and int(o["sol"].clique_proven_optimal) == 2
