@@ -115,8 +115,8 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src_3xN, const double* dst_3xN, 
 /* ---- stage 2: maximum clique ----------------------------------------------------------------
  * Replaces teaser::MaxCliqueSolver::findMaxClique (teaser/src/graph.cc:12-125) including the PMC
  * library calls it makes.  mode: 0 PMC_EXACT, 1 PMC_HEU, 2 KCORE_HEU.  clique: capacity n, returned
- * sorted ascending (solve() sorts it, registration.cc:636).  *proven_optimal = 1 when the search
- * proved maximality. */
+ * sorted ascending (solve() sorts it, registration.cc:636).  *proven_optimal: 1 / 2 / 0 with the meaning of
+ * tzr_solution.clique_proven_optimal. */
 int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, double kcore_heuristic_threshold,
                    double time_limit_s, int32_t* clique, int32_t* clique_size, int32_t* proven_optimal);
 

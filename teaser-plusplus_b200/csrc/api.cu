@@ -663,7 +663,7 @@ int tzr_max_clique(tzr_ctx* ctx, const uint64_t* adj_bits, int n, int mode, doub
   if (L > 0) CK(cudaMemcpy(clique, bt.clq, (size_t)L * sizeof(int32_t), cudaMemcpyDeviceToHost));
   std::sort(clique, clique + L);  // registration.cc:636
   *clique_size = L;
-  if (proven_optimal) *proven_optimal = (mode == 0 && !(fl & 1)) ? 1 : 0;
+  if (proven_optimal) *proven_optimal = (mode == 0 && !(fl & 1)) ? ((fl & 12) ? 2 : 1) : 0;  // as tzr_solution
   return TZR_OK;
 }
 
