@@ -1,55 +1,61 @@
-"""`teaserpp_python` for the B200-native solve() path: same public names as the reference package
-(python/teaserpp_python/__init__.py), certifier classes included."""
-from functools import wraps
-from typing import Callable, NamedTuple
+"""`teaserpp_python` for the B200-native path.
 
-from ._teaserpp import (
-    OMP_MAX_THREADS,
-    CertificationResult,
-    DRSCertifier,
-    EigSolverType,
-    InlierGraphFormulation,
-    InlierSelectionMode,
-    RegistrationSolution,
-    RobustRegistrationSolver,
-    RotationEstimationAlgorithm,
+Public surface = the reference package's (python/teaserpp_python/__init__.py): the pybind11 classes re-exported from
+`_teaserpp`, the v1.0 enum aliases on the solver / certifier classes, `RobustRegistrationSolverParams` (a named tuple
+of the fourteen constructor arguments with the reference's defaults, in constructor order) and the `params` attribute
+that hands back the positional arguments a solver object was built with.
+"""
+import collections
+import functools
+
+from . import _teaserpp as _ext
+
+# ---- re-exports -----------------------------------------------------------------------------------------------------
+_PUBLIC = ("OMP_MAX_THREADS", "CertificationResult", "DRSCertifier", "EigSolverType", "InlierGraphFormulation",
+           "InlierSelectionMode", "RegistrationSolution", "RobustRegistrationSolver", "RotationEstimationAlgorithm")
+globals().update({name: getattr(_ext, name) for name in _PUBLIC})
+
+# ---- v1.0 spellings of the enums, kept as class attributes ----------------------------------------------------------
+for _owner, _alias, _enum in ((_ext.RobustRegistrationSolver, "ROTATION_ESTIMATION_ALGORITHM", "RotationEstimationAlgorithm"),
+                              (_ext.RobustRegistrationSolver, "INLIER_SELECTION_MODE", "InlierSelectionMode"),
+                              (_ext.RobustRegistrationSolver, "INLIER_GRAPH_FORMULATION", "InlierGraphFormulation"),
+                              (_ext.DRSCertifier, "EIG_SOLVER_TYPE", "EigSolverType")):
+    setattr(_owner, _alias, getattr(_ext, _enum))
+
+# ---- constructor arguments as a named tuple (field order = the 14-argument constructor, registration.h:524-539) -----
+_CTOR_ARGS = collections.OrderedDict(
+    noise_bound=0.01,
+    cbar2=1,
+    estimate_scaling=True,
+    rotation_estimation_algorithm=_ext.RotationEstimationAlgorithm.GNC_TLS,
+    rotation_gnc_factor=1.4,
+    rotation_max_iterations=100,
+    rotation_cost_threshold=1e-6,
+    rotation_tim_graph=_ext.InlierGraphFormulation.CHAIN,
+    inlier_selection_mode=_ext.InlierSelectionMode.PMC_EXACT,
+    kcore_heuristic_threshold=0.5,
+    use_max_clique=True,
+    max_clique_exact_solution=True,
+    max_clique_time_limit=3600,
+    max_clique_num_threads=_ext.OMP_MAX_THREADS,
 )
-
-# v1.0 aliases (reference __init__.py:17-20)
-RobustRegistrationSolver.ROTATION_ESTIMATION_ALGORITHM = RotationEstimationAlgorithm
-RobustRegistrationSolver.INLIER_SELECTION_MODE = InlierSelectionMode
-RobustRegistrationSolver.INLIER_GRAPH_FORMULATION = InlierGraphFormulation
-DRSCertifier.EIG_SOLVER_TYPE = EigSolverType
+RobustRegistrationSolverParams = collections.namedtuple("RobustRegistrationSolverParams", list(_CTOR_ARGS),
+                                                        defaults=list(_CTOR_ARGS.values()))
 
 
-class RobustRegistrationSolverParams(NamedTuple):
-    noise_bound: float = 0.01
-    cbar2: float = 1
-    estimate_scaling: bool = True
-    rotation_estimation_algorithm: RotationEstimationAlgorithm = RotationEstimationAlgorithm.GNC_TLS
-    rotation_gnc_factor: float = 1.4
-    rotation_max_iterations: int = 100
-    rotation_cost_threshold: float = 1e-6
-    rotation_tim_graph: InlierGraphFormulation = InlierGraphFormulation.CHAIN
-    inlier_selection_mode: InlierSelectionMode = InlierSelectionMode.PMC_EXACT
-    kcore_heuristic_threshold: float = 0.5
-    use_max_clique: bool = True
-    max_clique_exact_solution: bool = True
-    max_clique_time_limit: int = 3600
-    max_clique_num_threads: int = OMP_MAX_THREADS
+# ---- solver.params: whatever positional arguments the object was constructed with -----------------------------------
+def _install_params_attribute(cls):
+    ctor = cls.__init__
+
+    @functools.wraps(ctor)
+    def recording_ctor(obj, *positional, **named):
+        ctor(obj, *positional, **named)
+        obj._params = positional
+
+    cls.__init__ = recording_ctor
+    cls.params = property(lambda obj: obj._params)
 
 
-def _remember_ctor_args(f: Callable[..., None]):
-    @wraps(f)
-    def wrapper(self, *args, **kwargs):
-        f(self, *args, **kwargs)
-        self._params = args
+_install_params_attribute(_ext.RobustRegistrationSolver)
 
-    return wrapper
-
-
-RobustRegistrationSolver.__init__ = _remember_ctor_args(RobustRegistrationSolver.__init__)
-RobustRegistrationSolver.params = property(lambda self: self._params)
-
-__all__ = ["OMP_MAX_THREADS", "InlierGraphFormulation", "InlierSelectionMode", "RegistrationSolution",
-           "RobustRegistrationSolver", "RotationEstimationAlgorithm", "RobustRegistrationSolverParams"]
+__all__ = list(_PUBLIC) + ["RobustRegistrationSolverParams"]
