@@ -1223,7 +1223,11 @@ __global__ void clique_resume_kernel(Batch bt) {
 
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches) {
   const int n = bt.n;
-  static bool attr_done = false;
+  // per device: a process may hold contexts on several GPUs
+  static bool attr_done_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_done = attr_done_dev[dev & 63];
   if (!attr_done) {
     cudaFuncSetAttribute(clique_heur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(clique_peel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -629,10 +629,12 @@ __global__ void __launch_bounds__(kRTThreads) rot_trans_kernel(Batch bt, tzr_par
 }
 
 void launch_rot_trans(const Batch& bt, const tzr_params& p, int use_clique, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done_dev[64] = {};  // per device: a process may hold contexts on several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done_dev[dev & 63]) {
     cudaFuncSetAttribute(rot_trans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_done = true;
+    attr_done_dev[dev & 63] = true;
   }
   int mode = p.inlier_selection_mode;
   if (!p.use_max_clique) mode = 3;
