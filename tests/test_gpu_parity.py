@@ -859,3 +859,22 @@ def test_dense_graph_is_closed_by_the_vertex_cover_bound(ctx):
     o = orc.solve(S, D, orc.default_params(noise_bound=0.05, cbar2=1.0, estimate_scaling=0,
                                            rotation_cost_threshold=1e-12, max_clique_time_limit=600.0))
     assert len(o["clique"]) == 597 and int(o["sol"].clique_proven_optimal) == 2
+
+
+def test_dense_small_instance_same_size_as_oracle(ctx):
+    """A 360-point dense instance (tests/test_oracle_dense_cpu.py checks the restatement's answer against a MILP):
+    the device returns a valid clique of the same, maximum, size."""
+    rng = np.random.default_rng(5)
+    n, n_out = 360, 110
+    src = rng.uniform(0, 0.15, size=(n, 3))
+    dst = src + (rng.random((n, 3)) - 0.5) * 0.1
+    dst[:n_out] += 7.0
+    bits, deg, ne = ctx.graph_build(src, dst, 0.1)
+    obits, _, _ = orc.build_graph_bits(src, dst, 0.05)
+    assert np.array_equal(bits, obits)
+    c, proven = ctx.max_clique(bits, n, mode=0, time_limit=120.0)
+    oc, info = orc.max_clique_bits(obits, n, mode=0, time_limit=300.0)
+    A = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
+    assert A[np.ix_(c, c)].sum() == len(c) * (len(c) - 1)
+    assert proven and not info["timed_out"]
+    assert len(c) == len(oc)
