@@ -1,6 +1,5 @@
 // B200 build of the reference's C++ quick-start (examples/teaser_cpp_ply/teaser_cpp_ply.cc): the solver-facing
-// lines (Params, constructor, solve, getSolution) are written exactly as a TEASER++ user writes them; only the PLY
-// reader (tinyply in the reference) is replaced by a 20-line ASCII parser.
+// lines (PLYReader, Params, constructor, solve, getSolution) are written exactly as a TEASER++ user writes them.
 //   usage: example_cpp_ply <bun_zipper_res3.ply>
 #include <chrono>
 #include <cmath>
@@ -10,6 +9,7 @@
 #include <sstream>
 #include <string>
 
+#include <teaser/ply_io.h>
 #include <teaser/registration.h>
 
 constexpr double NOISE_BOUND = 0.001;
@@ -17,36 +17,27 @@ constexpr int N_OUTLIERS = 1700;
 constexpr double OUTLIER_TRANSLATION_LB = 5;
 constexpr double OUTLIER_TRANSLATION_UB = 10;
 
-static teaser::Mat3X read_ascii_ply(const std::string& path) {
-  std::ifstream f(path);
-  if (!f) throw std::runtime_error("cannot open " + path);
-  std::string line;
-  long nv = 0;
-  while (std::getline(f, line)) {
-    std::istringstream is(line);
-    std::string a, b;
-    is >> a >> b;
-    if (a == "element" && b == "vertex") is >> nv;
-    if (a == "end_header") break;
-  }
-  teaser::Mat3X m(3, nv);
-  for (long i = 0; i < nv; ++i) {
-    float x, y, z;
-    std::getline(f, line);
-    std::istringstream is(line);
-    is >> x >> y >> z;
-    m(0, i) = x; m(1, i) = y; m(2, i) = z;
-  }
-  return m;
-}
-
 int main(int argc, char** argv) {
   if (argc < 2) {
     std::cerr << "usage: " << argv[0] << " bun_zipper_res3.ply\n";
     return 2;
   }
-  teaser::Mat3X src = read_ascii_ply(argv[1]);
-  const int N = static_cast<int>(src.cols());
+  // Load the .ply file (teaser_cpp_ply.cc:44-55)
+  teaser::PLYReader reader;
+  teaser::PointCloud src_cloud;
+  auto status = reader.read(argv[1], src_cloud);
+  if (status != 0) {
+    std::cerr << "cannot read " << argv[1] << "\n";
+    return 2;
+  }
+  const int N = static_cast<int>(src_cloud.size());
+  // Convert the point cloud to Eigen
+  teaser::Mat3X src(3, N);
+  for (int i = 0; i < N; ++i) {
+    src(0, i) = src_cloud[i].x;
+    src(1, i) = src_cloud[i].y;
+    src(2, i) = src_cloud[i].z;
+  }
   Eigen::Matrix3d R;
   R << 9.96926560e-01, 6.68735757e-02, -4.06664421e-02,
       -6.61289946e-02, 9.97617877e-01, 1.94008687e-02,

@@ -9,6 +9,7 @@ for f in objectIn.csv sceneIn.csv rotation_only_src.csv translation_test_v1_inli
   cp "$REF/test/teaser/data/registration_test/$f" "$HERE/registration_test/"
 done
 cp "$REF/examples/example_data/bun_zipper_res3.ply" "$HERE/"
+cp "$REF/test/teaser/data/cube.ply" "$HERE/"
 cp "$REF/test/teaser/data/bunny.pcd" "$REF/test/teaser/data/bunny_fpfh.csv" "$HERE/"
 cp -r "$REF/test/teaser/data/certification_small_instances" "$REF/test/teaser/data/certification_large_instances" "$HERE/"
 chmod -R u+w "$HERE"

@@ -70,3 +70,16 @@ def test_mex_shim_compiles_against_stub():
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.check_call([cxx, "-std=c++17", "-fsyntax-only", "-DTZR_MEX_SYNTAX_CHECK", "-I", mex,
                            "-I", os.path.join(ROOT, "include"), os.path.join(mex, "teaser_mex.cc")])
+
+
+def test_ply_io_roundtrip(tmp_path):
+    """teaser::PLYReader / PLYWriter of the façade (reference: test/teaser/io-test.cc) — host-only code, runs here."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = str(tmp_path / "ply_io_test")
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I", os.path.join(HOST, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "ply_io_test.cc"), os.path.join(HOST, "src", "ply_io.cc"),
+                           "-o", exe])
+    golden = os.path.join(ROOT, "tests", "golden")
+    out = subprocess.run([exe, os.path.join(golden, "cube.ply"), os.path.join(golden, "bun_zipper_res3.ply"),
+                          str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
