@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — registrations/sec of the TEASER++ solve() hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+    python bench.py --gpus N --steps K --warmup W [--config C2]   # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...         # the reference algorithm on the host cores
 
-Workload (config.workload): BASELINE config C2 — synthetic N=5000 correspondences, 95 % outliers
-("ball" outlier model), fixed scale, GNC-TLS, PMC_EXACT — as a batch of independent problems
-per step per GPU (weak scaling: every rank owns its own batch; no collective on the data path).
+--config selects one of the BASELINE.json configurations; the default, C2, is the one the metric is
+quoted on.  All use fixed scale (what every reference example uses) unless --estimate-scaling is given.
+    C1      bunny, N=1889, 1700 outlier draws (teaser_cpp_ply; README's 0.787 s datum)       single problem
+    C2      N=5000, 95 % outliers, "ball" outlier model                                        batch/GPU, weak scaling
+    C2cube  N=5000, 95 % outliers, "in-cube" outliers (real branch-and-bound in the clique)   batch/GPU, weak scaling
+    C3      N=10000, 99 % outliers, in-cube (max-clique stress)                                batch/GPU, weak scaling
+    C4      4096 problems x N=2000, 90 % outliers, sharded b mod G                            fixed batch, strong scaling
+    C5      256 problems x N=8000, 97 % outliers (3DMatch shape), sharded b mod G             fixed batch, strong scaling
 
-A "step" = one pass of solve() over one batch of --batch problems per GPU.
-  value : registrations/s with the inputs already resident in HBM (tzr_solve_batch_dev), CUDA-event timed.
-  e2e   : same metric through the host-pointer C-ABI call (tzr_solve_batch): pinned host inputs are copied
-          host->device inside the timed region and the solutions + clique index sets are read back.
-Inputs per step are larger than L2 (B*240 KB >= 246 MB at the default batch of 1024), so no L2 flush is needed.
+A "step" = one pass of solve() over this rank's batch.
+  value : registrations/s with the inputs already resident in HBM (tzr_solve_batch_dev), CUDA-event timed, no host
+          synchronisation between steps (stage events are kept by the library and read after the loop).
+  e2e   : same metric through the host-pointer C-ABI call (tzr_solve_batch): page-locked host inputs are copied
+          host->device inside the timed region, solutions + clique index sets are read back; `pageable` repeats it
+          from ordinary (numpy) host memory.
+  latency : one problem through tzr_solve (the drop-in solve() shape), p50 over >= 20 calls.
+Inputs per step are larger than L2 for the batch configs; for the small ones an L2 flush (256 MB write) runs
+between steps and is excluded from the per-stage kernel times but not from ms_per_step — see config.l2.
 """
 import argparse
-import ctypes as C
 import importlib
 import json
 import os
@@ -30,8 +38,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N_C2 = 5000
-OUTLIER_RATIO = 0.95
+CONFIGS = {
+    # name: (synth cfg, n, default batch per GPU (weak) or total batch (strong), scaling, description)
+    "C1": dict(n=1889, batch=1, scaling="weak", desc="C1 bunny: N=1889 correspondences, 1700 outlier draws (teaser_cpp_ply), nb=0.001"),
+    "C2": dict(n=5000, batch=1024, scaling="weak", desc="C2: N=5000 correspondences, 95% outliers (ball)"),
+    "C2cube": dict(n=5000, batch=256, scaling="weak", desc="C2cube: N=5000 correspondences, 95% outliers (in-cube)"),
+    "C3": dict(n=10000, batch=32, scaling="weak", desc="C3: N=10000 correspondences, 99% outliers (in-cube, max-clique stress)"),
+    "C3ball": dict(n=10000, batch=64, scaling="weak", desc="C3ball: N=10000 correspondences, 99% outliers (ball)"),
+    "C4": dict(n=2000, batch=4096, scaling="strong", desc="C4: 4096 problems x N=2000, 90% outliers (ball), sharded b mod G"),
+    "C5": dict(n=8000, batch=256, scaling="strong", desc="C5: 256 problems x N=8000, 97% outliers (3DMatch shape), sharded b mod G"),
+}
 
 
 def bytes_graph(n):
@@ -54,7 +70,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,7 +84,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
@@ -85,50 +101,77 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # median of the upper half = clocks under load (the sampler also sees idle gaps)
-        s = sorted(sm)
+        s = sorted(sm)  # median of the upper half = clocks under load (the sampler also sees idle gaps)
         return {"sm_mhz": float(np.median(s[len(s) // 2:])), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
-def make_batch(B, base_seed, synth):
-    src = np.empty((B, N_C2, 3))
-    dst = np.empty((B, N_C2, 3))
-    inl = []
-    nb = None
-    for b in range(B):
-        pr = synth.make_problem(N_C2, OUTLIER_RATIO, 5000 * 1000 + base_seed + b, "ball")
-        src[b], dst[b] = pr["src"], pr["dst"]
+def problem(cfg, b, synth):
+    if cfg == "C1":
+        return synth.bunny_problem(os.path.join(synth.GOLDEN_DIR, "bun_zipper_res3.ply"), seed=1889 + b)
+    return synth.config_problem(cfg, b)
+
+
+def make_batch(cfg, idx, synth):
+    n = CONFIGS[cfg]["n"]
+    src = np.empty((len(idx), n, 3))
+    dst = np.empty((len(idx), n, 3))
+    inl, nb = [], None
+    for k, b in enumerate(idx):
+        pr = problem(cfg, int(b), synth)
+        src[k], dst[k] = pr["src"], pr["dst"]
         inl.append(pr["inliers"])
         nb = pr["noise_bound"]
     return src, dst, inl, nb
 
 
-def solver_params(mod, nb):
-    return mod.default_params(noise_bound=nb, cbar2=1.0, estimate_scaling=0, rotation_estimation_algorithm=0,
-                              rotation_gnc_factor=1.4, rotation_max_iterations=100, rotation_cost_threshold=1e-12,
-                              rotation_tim_graph=0, inlier_selection_mode=0)
+def solver_params(mod, cfg, nb, estimate_scaling):
+    # C1: teaser_cpp_ply.cc:76-88 (cost threshold 0.005); the others: registration-benchmark.cc:193 (1e-12)
+    return mod.default_params(noise_bound=nb, cbar2=1.0, estimate_scaling=1 if estimate_scaling else 0,
+                              rotation_estimation_algorithm=0, rotation_gnc_factor=1.4, rotation_max_iterations=100,
+                              rotation_cost_threshold=0.005 if cfg == "C1" else 1e-12, rotation_tim_graph=0,
+                              inlier_selection_mode=0)
 
 
-def cpu_reference_sample(n_problems, seed0, synth, budget_s=25.0):
-    """Times the CPU restatement of the reference algorithm (oracle, OpenMP on all host cores) on a bounded
-    sample of the same workload.  Returns (regs_per_s, cores, n_done, seconds)."""
+def workload_string(cfg, estimate_scaling, extra=""):
+    sc = "unknown scale (estimate_scaling=true, the Params default)" if estimate_scaling else "fixed scale"
+    return f"{CONFIGS[cfg]['desc']}, {sc}, GNC-TLS, PMC_EXACT{extra}"
+
+
+ORC_STAGES = ("tims", "scale_test", "graph", "clique", "rotation", "translation", "total")
+
+
+def oracle_threads(orc, want):
+    """Set and report the OpenMP thread count of the CPU restatement explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    L = orc.lib()
+    if hasattr(L, "orc_set_num_threads"):
+        L.orc_set_num_threads(int(want))
+    return int(L.orc_num_threads())
+
+
+def cpu_sample(cfg, estimate_scaling, synth, seed0, max_problems, budget_s, threads):
+    """Times the CPU restatement of the reference algorithm (oracle) on a bounded sample of the workload.
+    Returns dict(value, cores, done, seconds, stage_ms (mean per problem), p50_ms)."""
     import oracle_lib as orc
-    cores = orc.lib().orc_num_threads()
-    pr = synth.make_problem(N_C2, OUTLIER_RATIO, 5000 * 1000 + seed0, "ball")
-    p = solver_params(orc, pr["noise_bound"])
+    cores = oracle_threads(orc, threads)
+    pr = problem(cfg, seed0, synth)
+    p = solver_params(orc, cfg, pr["noise_bound"], estimate_scaling)
     orc.solve(pr["src"], pr["dst"], p)  # warm-up (page faults, thread pool)
-    done, t_total = 0, 0.0
-    for i in range(n_problems):
-        pr = synth.make_problem(N_C2, OUTLIER_RATIO, 5000 * 1000 + seed0 + 1 + i, "ball")
+    done, t_total, times = 0, 0.0, []
+    stage = np.zeros(7)
+    for i in range(max_problems):
+        pr = problem(cfg, seed0 + 1 + i, synth)
         t0 = time.perf_counter()
         out = orc.solve(pr["src"], pr["dst"], p)
-        t_total += time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+        t_total += dt
+        times.append(dt * 1e3)
+        stage += np.asarray(out.get("stage_ms", np.zeros(8)))[:7]
         done += 1
-        assert out["valid"]
         if t_total > budget_s:
             break
-    return done / t_total, cores, done, t_total
+    return dict(value=done / t_total, cores=cores, done=done, seconds=t_total,
+                stage_ms={k: float(v / done) for k, v in zip(ORC_STAGES, stage)}, p50_ms=float(np.median(times)))
 
 
 def run_reference(args, rank, world):
@@ -137,35 +180,34 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     synth = importlib.import_module("teaser-plusplus_b200.synth")
-    import oracle_lib as orc
-    cores = orc.lib().orc_num_threads()
+    cfg = args.config
+    threads = os.cpu_count() or 1
     per_step = max(1, args.ref_problems_per_step)
-    pr = synth.make_problem(N_C2, OUTLIER_RATIO, 5000 * 1000, "ball")
-    p = solver_params(orc, pr["noise_bound"])
-    for w in range(min(args.warmup, 1) or 1):
-        orc.solve(pr["src"], pr["dst"], p)
-    t_total, done = 0.0, 0
-    for k in range(args.steps):
-        for i in range(per_step):
-            q = synth.make_problem(N_C2, OUTLIER_RATIO, 5000 * 1000 + 1 + k * per_step + i, "ball")
-            t0 = time.perf_counter()
-            orc.solve(q["src"], q["dst"], p)
-            t_total += time.perf_counter() - t0
-            done += 1
-    v = done / t_total
+    # bounded: at most steps*per_step problems or ~90 s of CPU work
+    s = cpu_sample(cfg, args.estimate_scaling, synth, 0, args.steps * per_step, 90.0, threads)
+    v = s["value"]
+    steps_done = max(1, s["done"] // per_step)
     line = {
         "impl": "reference", "metric": "registrations/sec", "value": v, "unit": "registrations/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: N={N_C2} correspondences, {int(OUTLIER_RATIO*100)}% outliers (ball), fixed scale, "
-                               f"GNC-TLS, PMC_EXACT; {per_step} problem(s) per step on the host cores"},
-        "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
-                         "sample": f"{done} problems of the C2 workload, solved back to back with OpenMP on {cores} "
-                                   f"threads (reference restatement; Eigen/PMC unavailable so the true reference "
-                                   f"cannot be built)"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s["seconds"] / steps_done,
+        "higher_is_better": True, "scaling": CONFIGS[cfg]["scaling"], "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_string(cfg, args.estimate_scaling),
+                   "sample": f"{per_step} problem(s) per step on the host cores"},
+        "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": s["cores"], "kind": "port",
+                         "omp_threads_set_explicitly": True, "host_cpus": os.cpu_count(),
+                         "sample": f"{s['done']} problems of the {cfg} workload ({s['seconds']:.1f} s), solved back to "
+                                   f"back with OpenMP on {s['cores']} threads (reference restatement; Eigen/PMC "
+                                   f"unavailable so the true reference cannot be built)",
+                         "stage_ms_per_problem": s["stage_ms"], "latency_ms_p50": s["p50_ms"],
+                         "note": "serial stages of the reference (scale test registration.cc:427-443, graph loop "
+                                 ":614-619) bound the multi-thread speed-up; see stage_ms_per_problem"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if cfg == "C1":
+        line["cpu_baseline"]["upstream_published"] = {"seconds": 0.787, "source": "reference README.md:75-77 (teaser_cpp_ply, "
+                                                      "unspecified CPU); timed like teaser_cpp_ply.cc:91-93"}
     print(json.dumps(line), flush=True)
 
 
@@ -175,9 +217,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="problems per step per GPU")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--estimate-scaling", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="problems per step per GPU (weak configs) / in total (C4, C5)")
     ap.add_argument("--ref-problems-per-step", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-problems", type=int, default=16)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -198,37 +243,54 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     capi = importlib.import_module("teaser-plusplus_b200.capi")
     synth = importlib.import_module("teaser-plusplus_b200.synth")
+    shard = importlib.import_module("teaser-plusplus_b200.shard")
+    cfg = args.config
+    C = CONFIGS[cfg]
+    n = C["n"]
     W = max(args.warmup, 3)
     K = args.steps
-    B = args.batch
+    strong = C["scaling"] == "strong"
+    Btot = args.batch or C["batch"]
+    if strong:   # fixed batch, problem b on rank b mod G
+        idx = shard.shard_indices(Btot, rank, world)
+        global_batch = Btot
+    else:        # every rank its own batch (weak scaling)
+        idx = np.arange(Btot, dtype=np.int64) + rank * 100000
+        global_batch = Btot * world
+    B = len(idx)
 
-    # ---- synthetic inputs: each rank its own batch (weak scaling), pinned host copies + device copies
-    src_h, dst_h, inliers, nb = make_batch(B, rank * 100000, synth)
-    src_pin = torch.empty((B, N_C2, 3), dtype=torch.float64, pin_memory=True)
-    dst_pin = torch.empty((B, N_C2, 3), dtype=torch.float64, pin_memory=True)
+    # ---- synthetic inputs: pinned host copies + device copies
+    src_h, dst_h, inliers, nb = make_batch(cfg, idx, synth)
+    src_pin = torch.empty((B, n, 3), dtype=torch.float64, pin_memory=True)
+    dst_pin = torch.empty((B, n, 3), dtype=torch.float64, pin_memory=True)
     src_pin.numpy()[...] = src_h
     dst_pin.numpy()[...] = dst_h
     src_d = src_pin.cuda(non_blocking=False)
     dst_d = dst_pin.cuda(non_blocking=False)
     sol_d = torch.zeros(B * capi.SOLUTION_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-    clq_d = torch.zeros((B, N_C2), dtype=torch.int32, device="cuda")
-    params = solver_params(capi, nb)
+    clq_d = torch.zeros((B, n), dtype=torch.int32, device="cuda")
+    params = solver_params(capi, cfg, nb, args.estimate_scaling)
     ctx = capi.Context(local_rank)
-    if os.environ.get("TZR_FLAGS"):  # debug / A-B switches of the library (e.g. 8 = previous graph kernel)
-        ctx.set_flags(int(os.environ["TZR_FLAGS"]))
+    base_flags = int(os.environ.get("TZR_FLAGS", "0"))  # debug / A-B switches of the library (512 = CUDA-core graph kernel)
+    ctx.set_flags(base_flags)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    # L2 flush between steps for working sets that would otherwise sit in the 126 MB L2
+    step_bytes = B * (48 * n + n * ((n + 127) // 128) * 16)
+    flush = None
+    if step_bytes < 512e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def step_dev():
-        ctx.solve_batch_dev(params, B, N_C2, src_d.data_ptr(), dst_d.data_ptr(), sol_d.data_ptr(), clq_d.data_ptr())
+        ctx.solve_batch_dev(params, B, n, src_d.data_ptr(), dst_d.data_ptr(), sol_d.data_ptr(), clq_d.data_ptr())
 
     src_np, dst_np = src_pin.numpy(), dst_pin.numpy()  # page-locked host buffers
     h_sols = np.zeros(B, dtype=capi.SOLUTION_DTYPE)
-    h_clq = np.zeros((B, N_C2), dtype=np.int32)
+    h_clq = np.zeros((B, n), dtype=np.int32)
 
-    def step_host():
+    def step_host(s=src_np, d=dst_np):
         # the public host-pointer call: H2D of this step's inputs, all kernels, D2H of solutions + clique sets
-        return ctx.solve_batch_array(src_np, dst_np, params, cliques_out=h_clq, sols_out=h_sols)
+        return ctx.solve_batch_array(s, d, params, cliques_out=h_clq, sols_out=h_sols)
 
     def barrier():
         if use_dist:
@@ -239,36 +301,50 @@ def main():
     for _ in range(W):
         step_dev()
     ctx.synchronize()
-    # correctness of the timed path itself: identical inlier sets on the whole batch
     sols = np.frombuffer(sol_d.cpu().numpy().tobytes(), dtype=capi.SOLUTION_DTYPE)
     clq = clq_d.cpu().numpy()
     n_ok = sum(int(np.array_equal(clq[b, :sols[b]["clique_size"]], inliers[b])) for b in range(B))
+    # one untimed step with the debug counters on: exact re-checks of the graph filter, clique search nodes
+    ctx.set_flags(base_flags | 4)
+    step_dev()
+    ctx.synchronize()
+    counters = ctx.debug_counters()
+    ctx.set_flags(base_flags)
+    step_dev()
+    ctx.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- timed region 1: device-resident inputs
+    # ---- timed region 1: device-resident inputs, no host synchronisation between steps
     barrier()
     l0 = ctx.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    graph_ms = []
-    stage_acc = {"prep": 0.0, "graph": 0.0, "clique": 0.0, "rot_trans": 0.0}
+    ctx.stage_log(True)
     ev_begin, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev_begin.record(stream)
         for _ in range(K):
+            if flush is not None:
+                flush.fill_(1)
             step_dev()
-            ev1.record(stream)
-            ev1.synchronize()  # per-step sync only to read this step's stage events (graph-kernel time for the roofline)
-            st = ctx.last_stage_ms()
-            graph_ms.append(st["graph"])
-            for k_ in stage_acc:
-                stage_acc[k_] += st[k_]
         ev_end.record(stream)
         ev_end.synchronize()
-        t_dev = ev_begin.elapsed_time(ev_end)  # device time of exactly K steps, host gaps between steps included
+        t_dev = ev_begin.elapsed_time(ev_end)
+    stage_sum, n_calls = ctx.stage_log_read()
+    ctx.stage_log(False)
     barrier()
     launches = ctx.kernel_launches() - l0
-    # ---- timed region 2: end to end through the host-pointer C-ABI
+    t_flush = 0.0
+    if flush is not None:  # the flush writes are inside ev_begin..ev_end: measure them alone and take them out
+        with torch.cuda.stream(stream):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(K):
+                flush.fill_(1)
+            f1.record(stream)
+            f1.synchronize()
+            t_flush = f0.elapsed_time(f1)
+    t_dev_net = max(t_dev - t_flush, 1e-6)
+    # ---- timed region 2: end to end through the host-pointer C-ABI (pinned, then pageable host memory)
     for _ in range(2):
         step_host()
     barrier()
@@ -278,17 +354,35 @@ def main():
         hsols, hcl = step_host()
         t_e2e += (time.perf_counter() - t0) * 1e3
     barrier()
+    e2e_ok = sum(int(np.array_equal(hcl[b, :hsols[b]["clique_size"]], inliers[b])) for b in range(B))
+    src_pg, dst_pg = np.array(src_h, copy=True), np.array(dst_h, copy=True)  # ordinary pageable numpy memory
+    step_host(src_pg, dst_pg)
+    barrier()
+    t_pg = 0.0
+    for _ in range(K):
+        t0 = time.perf_counter()
+        step_host(src_pg, dst_pg)
+        t_pg += (time.perf_counter() - t0) * 1e3
+    barrier()
+    # ---- single-problem latency through tzr_solve (the shape of the reference's solve())
+    lat = []
+    for r in range(max(20, 3)):
+        b = r % B
+        t0 = time.perf_counter()
+        g1 = ctx.solve(src_h[b], dst_h[b], params)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat_stage = ctx.last_stage_ms()
     clocks = sampler.stop()
 
-    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([t_dev_net, t_e2e, t_pg], dtype=torch.float64, device="cuda")
     if use_dist:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev_max, t_e2e_max = float(tt[0]), float(tt[1])
-    e2e_ok = sum(int(np.array_equal(hcl[b, :hsols[b]["clique_size"]], inliers[b])) for b in range(B))
+    t_dev_max, t_e2e_max, t_pg_max = float(tt[0]), float(tt[1]), float(tt[2])
 
     if rank == 0:
-        value = world * K * B / (t_dev_max * 1e-3)
-        e2e = world * K * B / (t_e2e_max * 1e-3)
+        value = global_batch * K / (t_dev_max * 1e-3)
+        e2e = global_batch * K / (t_e2e_max * 1e-3)
+        e2e_pg = global_batch * K / (t_pg_max * 1e-3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -296,72 +390,83 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        g_ms = float(np.mean(graph_ms))
-        achieved = bytes_graph(N_C2) * B / (g_ms * 1e-3) / 1e9
+        g_ms = stage_sum["graph"] / max(n_calls, 1)   # graph stage per step (operand tiles + graph kernels), CUDA events
+        achieved = bytes_graph(n) * B / (g_ms * 1e-3) / 1e9
         traffic = None
-        issue = None
-        try:
-            # measured once with `ncu --set full` (profiles/graph_kernel_traffic.json), scaled to this launch's batch
+        try:  # measured once with `ncu --set full`, scaled to this launch's batch
             prof = json.load(open(os.path.join(ROOT, "profiles", "graph_kernel_traffic.json")))
-            traffic = prof.get("dram_bytes_per_problem") * B
-            # the binding resource of this kernel is the warp-instruction issue rate, not HBM: warp instructions of one
-            # launch (ncu count per problem x B) / live kernel time, against 4 issue slots per SM per clock
-            winst = prof["inst_executed"] / prof["batch"] * B
-            sm_mhz = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
-            issue_peak = 148 * 4 * sm_mhz * 1e6
-            issue = {"achieved_warp_inst_per_s": winst / (g_ms * 1e-3), "peak_warp_inst_per_s": issue_peak,
-                     "frac": winst / (g_ms * 1e-3) / issue_peak,
-                     "warp_inst_per_pair": prof["inst_executed"] / prof["batch"] / (N_C2 * (N_C2 - 1) / 2)}
+            if prof.get("n") == n:
+                traffic = prof.get("dram_bytes_per_problem") * B
         except Exception:
             pass
+        tc = not (base_flags & 512)
         line = {
             "metric": "registrations/sec", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": t_dev_max / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": t_dev_max / K, "higher_is_better": True, "scaling": C["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"C2: N={N_C2} correspondences, {int(OUTLIER_RATIO*100)}% outliers (ball), fixed scale, "
-                            f"GNC-TLS (cost_thr 1e-12), PMC_EXACT; batch {B} problems/step/GPU",
-                "global_batch": B * world, "parallelism": f"batch sharded over {world} GPU(s), no collective",
-                "l2": f"inputs larger than L2: {2 * B * N_C2 * 24 / 1e6:.0f} MB of points + "
-                      f"{B * N_C2 * 80 * 8 / 1e9:.2f} GB of adjacency per step (L2 = 126 MB); no flush",
-                "dtype_note": "FP64 predicate/GNC/TLS; graph stage classifies pairs with an FP32 interval filter "
-                              "and re-checks the ambiguous band in exact FP64 (bit-identical bitset)",
+                "workload": workload_string(cfg, args.estimate_scaling,
+                                            f"; {'total batch ' + str(global_batch) + ' sharded b mod G' if strong else 'batch ' + str(B) + ' problems/step/GPU'}"),
+                "name": cfg, "global_batch": global_batch,
+                "parallelism": f"batch sharded over {world} GPU(s), no collective",
+                "l2": (f"inputs larger than L2: {step_bytes / 1e6:.0f} MB of points + adjacency per step (L2 = 126 MB); no flush"
+                       if flush is None else
+                       f"working set {step_bytes / 1e6:.0f} MB per step: 256 MB L2 flush between steps (its {t_flush / K:.3f} ms "
+                       f"per step is subtracted from ms_per_step)"),
+                "dtype_note": "FP64 predicate/GNC/TLS; the graph stage classifies pairs from tensor-core (tf32x3 split) "
+                              "squared norms in FP32 and re-checks the undecided band in exact FP64 (bit-identical bitset)",
             },
-            "e2e": {"value": e2e, "unit": "registrations/s", "h2d_bytes_per_step": int(2 * B * N_C2 * 24),
+            "e2e": {"value": e2e, "unit": "registrations/s", "h2d_bytes_per_step": int(2 * B * n * 24),
                     # what tzr_solve_batch copies back: the solution records + the used prefix of every clique row
-                    "d2h_bytes_per_step": int(B * capi.SOLUTION_DTYPE.itemsize
-                                              + B * int(hsols["clique_size"].max()) * 4),
-                    "ms_per_step": t_e2e_max / K},
+                    "d2h_bytes_per_step": int(B * capi.SOLUTION_DTYPE.itemsize + B * int(hsols["clique_size"].max()) * 4),
+                    "ms_per_step": t_e2e_max / K, "host_memory": "page-locked, contiguous (zero-staging DMA)",
+                    "pageable": {"value": e2e_pg, "ms_per_step": t_pg_max / K,
+                                 "host_memory": "ordinary numpy arrays (staged through the context's pinned buffer)"}},
+            "latency": {"single_problem_ms_p50": float(np.median(lat)), "single_problem_ms_min": float(np.min(lat)),
+                        "calls": len(lat), "api": "tzr_solve (host pointers in, solution + clique + masks out)",
+                        "stage_ms_last_call": lat_stage},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "graph_strip2_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "graph_tc_kernel (+ tc_prep_kernel)" if tc else "graph_strip2_kernel",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": bytes_graph(N_C2) * B, "kernel_ms": g_ms, "issue": issue,
-                         "note": "issue-bound FP32 stage (12 FP32 ops as 6 packed FP32x2 instructions + 2 MUFU + 2 FSETP "
-                                 "per pair, ~60 op/B): the HBM fraction is reported because SURVEY §8d defines the "
-                                 "roofline of this stage against HBM; DRAM traffic is within 0.9x of algorithmic"},
-            "stage_ms_per_step": {k_: v / K for k_, v in stage_acc.items()},
+                         "algorithmic_bytes_per_launch": bytes_graph(n) * B, "kernel_ms": g_ms,
+                         "note": "graph stage = O(N^2) pair classification; SURVEY §8d defines its roofline against HBM "
+                                 "(algorithmic bytes: points in, packed bitset + degrees out).  The binding resource is "
+                                 "the per-pair arithmetic (1 MUFU + 6 issue slots per pair after moving the squared norms "
+                                 "to the tensor cores), not DRAM"},
+            "stage_ms_per_step": {k_: v / max(n_calls, 1) for k_, v in stage_sum.items()},
+            "counters": {"graph_exact_rechecks_per_problem": counters["filter_rechecks"] / B,
+                         "clique_search_nodes_per_problem": counters["clique_nodes"] / B},
             "parity": {"timed_batch_clique_equals_planted_inliers": f"{n_ok}/{B}",
                        "e2e_batch_clique_equals_planted_inliers": f"{e2e_ok}/{B}",
                        "note": "ground-truth check; a planted set can be strictly inside the maximum clique when an "
                                "outlier happens to be consistent with every inlier"},
         }
         # rotation / translation error vs the oracle on identical inputs (metric's second half) + CPU baseline
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
             import oracle_lib as orc
-            errs = []
-            for b in range(2):
-                o = orc.solve(src_h[b], dst_h[b], solver_params(orc, nb))
+            threads = oracle_threads(orc, os.cpu_count() or 1)
+            errs, t_par = [], time.perf_counter()
+            for b in range(min(B, args.parity_problems)):
+                o = orc.solve(src_h[b], dst_h[b], solver_params(orc, cfg, nb, args.estimate_scaling))
                 Rg = capi.rotation_from_solution_record(sols[b])
                 errs.append((synth.angular_error(o["R"], Rg), float(np.linalg.norm(o["t"] - sols[b]["translation"])),
-                             bool(np.array_equal(o["clique"], clq[b, :sols[b]["clique_size"]]))))
+                             bool(np.array_equal(o["clique"], clq[b, :sols[b]["clique_size"]])),
+                             abs(float(o["scale"]) - float(sols[b]["scale"]))))
+                if time.perf_counter() - t_par > 90.0:
+                    break
             line["parity"]["vs_oracle"] = {"rot_err_rad_max": max(e[0] for e in errs),
                                            "trans_err_m_max": max(e[1] for e in errs),
+                                           "scale_err_max": max(e[3] for e in errs),
                                            "clique_identical": all(e[2] for e in errs), "problems": len(errs)}
-            v, cores, done, secs = cpu_reference_sample(12, 777, synth)
-            line["cpu_baseline"] = {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
-                                    "sample": f"{done} problems of the same C2 workload ({secs:.1f} s), OpenMP on "
-                                              f"{cores} host threads, reference restatement (Eigen/PMC unavailable)"}
+            if world == 1:
+                s = cpu_sample(cfg, args.estimate_scaling, synth, 777, 24, 20.0, threads)
+                line["cpu_baseline"] = {"value": s["value"], "unit": "registrations/s", "cores": s["cores"], "kind": "port",
+                                        "sample": f"{s['done']} problems of the same {cfg} workload ({s['seconds']:.1f} s), "
+                                                  f"OpenMP on {s['cores']} host threads (set explicitly), reference "
+                                                  f"restatement (Eigen/PMC unavailable)",
+                                        "stage_ms_per_problem": s["stage_ms"], "latency_ms_p50": s["p50_ms"]}
         print(json.dumps(line), flush=True)
     ctx.close()
     if use_dist:

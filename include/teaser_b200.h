@@ -4,7 +4,7 @@
  * This is the drop-in boundary: plain C, caller-owned buffers, no STL / Eigen / torch types.
  * The reference has no FFI layer of its own; each entry point below names the
  * reference function(s) it replaces (paths relative to the reference tree).  The C++ facade
- * `teaser::RobustRegistrationSolver` (teaser-plusplus_b200/include/teaser/registration.h) and the
+ * `teaser::RobustRegistrationSolver` (teaser-plusplus_b200/host/include/teaser/registration.h) and the
  * Python module `teaserpp_python` call exactly these symbols; INTEGRATION.md shows the binding a
  * TEASER++ maintainer would add.
  *
@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TZR_ABI_VERSION 1
+#define TZR_ABI_VERSION 2
 
 typedef enum tzr_status {
   TZR_OK = 0,
@@ -236,13 +236,36 @@ int tzr_solve_batch_dev(tzr_ctx* ctx, const tzr_params* params, int B, int n, co
 /* Retrieve the adjacency bitset / degrees of problem b of the most recent solve on this context
  * (lazy materialisation of getInlierGraph(), registration.h:772). Host pointers. */
 int tzr_last_graph(tzr_ctx* ctx, int b, uint64_t* adj_bits, int32_t* degree);
+/* What tzr_last_graph would return: batch size and n of the retained solve (0, 0 if none), whether a graph was
+ * built (0 after inlier selection NONE: the reference never populates the graph, registration.cc:607-650, and
+ * tzr_last_graph then yields an empty adjacency), and a generation counter that changes with every call that
+ * rebuilds or invalidates the retained graph — callers that share a context (the C++ facade's per-thread context)
+ * compare it with the value they saw after their own solve before trusting tzr_last_graph. */
+int tzr_last_graph_info(const tzr_ctx* ctx, int32_t* B, int32_t* n, int32_t* has_graph, uint64_t* generation);
 
 /* Graph-stage timing of the most recent tzr_solve_batch_dev, in milliseconds, measured with CUDA
  * events on the context's stream (for the roofline line in bench.py). Requires a prior synchronize. */
 int tzr_last_stage_ms(tzr_ctx* ctx, double* prep_ms, double* graph_ms, double* clique_ms, double* rot_trans_ms);
+/* Stage-timing log: while enabled the context keeps the CUDA events of EVERY pipeline call instead of re-using
+ * them, so a benchmark loop can run without a host synchronisation per step; tzr_ctx_stage_log_read synchronises
+ * once, returns the sums {prep, graph, clique, rot+trans} in ms over all calls since the last read (or enable) and
+ * their count, and clears the log. */
+int tzr_ctx_stage_log(tzr_ctx* ctx, int enable);
+int tzr_ctx_stage_log_read(tzr_ctx* ctx, double* sums_ms4, int32_t* n_calls);
 
-/* Debug/verification switches: bit 0 = force the pure-FP64 graph predicate (no FP32 filter),
- * bit 1 = verify the FP32 filter against FP64 for every pair and count mismatches. */
+/* ---- multi-GPU ------------------------------------------------------------------------------
+ * tzr_solve_batch over several devices of one node from a single host call (independent problems,
+ * no exchange step, no collective): the library keeps one context per device, cuts the batch into contiguous
+ * shards balanced by sum n_b^2 and drives each shard from its own host thread.  devices == NULL or n_devices <= 0:
+ * every visible device.  Same argument meaning as tzr_solve_batch; thread-safe (calls are serialised). */
+int tzr_solve_batch_multi(const int32_t* devices, int n_devices, const tzr_params* params, int B, const int32_t* n,
+                          const double* const* src, const double* const* dst, tzr_solution* solutions,
+                          int32_t* cliques, int max_n);
+
+/* Debug/verification switches: bit 0 (1) = force the pure-FP64 graph predicate (no FP32 filter),
+ * bit 1 (2) = verify the FP32 / tensor-core filter against FP64 for every pair and count mismatches,
+ * bit 2 (4) = count exact re-checks and clique search nodes, bit 8 (256) = degrees by a separate pass,
+ * bit 9 (512) = CUDA-core graph kernel for every problem (no tensor-core path). */
 int tzr_ctx_set_flags(tzr_ctx* ctx, uint32_t flags);
 int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx);
 /* Number of pairs of the most recent graph build that needed the exact FP64 re-check. */

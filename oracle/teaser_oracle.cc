@@ -1175,6 +1175,15 @@ struct orc_solution {
 
 int orc_num_threads() { return max_threads(); }
 
+// bench.py sets the OpenMP thread count explicitly (torchrun exports OMP_NUM_THREADS=1 to its children)
+void orc_set_num_threads(int t) {
+#ifdef _OPENMP
+  if (t > 0) omp_set_num_threads(t);
+#else
+  (void)t;
+#endif
+}
+
 void orc_compute_tims(const double* v, int64_t n, double* tims, int32_t* map) { compute_tims(v, n, tims, map); }
 
 void orc_scale_inliers_selector(const double* src_tims, const double* dst_tims, int64_t K, double noise_bound,

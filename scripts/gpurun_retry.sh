@@ -1,0 +1,11 @@
+#!/bin/bash
+# usage: gpurun_retry.sh <timeout_s> <command...>  — retries while the pod answers "busy" (exit 3, nothing charged)
+T=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  echo "[retry] attempt $i answered busy; sleeping 90 s"
+  sleep 90
+done
+exit 3

@@ -94,7 +94,8 @@ _SYMBOLS = [
     "tzr_solve", "tzr_solve_batch", "tzr_solve_batch_dev", "tzr_last_graph", "tzr_last_stage_ms",
     "tzr_ctx_set_flags", "tzr_ctx_filter_mismatches", "tzr_ctx_filter_rechecks", "tzr_ctx_debug_counters",
     "tzr_match_correspondences", "tzr_feature_nn", "tzr_compute_fpfh", "tzr_certifier_params_default", "tzr_certify",
-    "tzr_certifier_initial_matrix", "tzr_certifier_dual_projection",
+    "tzr_certifier_initial_matrix", "tzr_certifier_dual_projection", "tzr_last_graph_info", "tzr_ctx_stage_log",
+    "tzr_ctx_stage_log_read", "tzr_solve_batch_multi",
 ]
 
 
@@ -143,6 +144,11 @@ def lib():
     L.tzr_solve_batch_dev.argtypes = [vp, C.POINTER(Params), C.c_int, C.c_int, vp, vp, vp, vp]
     L.tzr_last_graph.argtypes = [vp, C.c_int, u64p, i32p]
     L.tzr_last_stage_ms.argtypes = [vp, dp, dp, dp, dp]
+    L.tzr_last_graph_info.argtypes = [vp, i32p, i32p, i32p, u64p]
+    L.tzr_ctx_stage_log.argtypes = [vp, C.c_int]
+    L.tzr_ctx_stage_log_read.argtypes = [vp, dp, i32p]
+    L.tzr_solve_batch_multi.argtypes = [i32p, C.c_int, C.POINTER(Params), C.c_int, i32p, C.POINTER(dp), C.POINTER(dp),
+                                        C.POINTER(Solution), i32p, C.c_int]
     L.tzr_ctx_set_flags.argtypes = [vp, C.c_uint32]
     L.tzr_ctx_filter_mismatches.argtypes = [vp]
     L.tzr_ctx_filter_mismatches.restype = C.c_int64
@@ -241,6 +247,21 @@ class Context:
         v = [C.c_double() for _ in range(4)]
         self._ck(lib().tzr_last_stage_ms(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3])))
         return dict(prep=v[0].value, graph=v[1].value, clique=v[2].value, rot_trans=v[3].value)
+
+    def stage_log(self, enable: bool):
+        """Keep the stage events of every call (no host sync per step); read them with stage_log_read()."""
+        self._ck(lib().tzr_ctx_stage_log(self._h, 1 if enable else 0))
+
+    def stage_log_read(self):
+        v = (C.c_double * 4)()
+        calls = C.c_int32()
+        self._ck(lib().tzr_ctx_stage_log_read(self._h, v, C.byref(calls)))
+        return dict(prep=v[0], graph=v[1], clique=v[2], rot_trans=v[3]), int(calls.value)
+
+    def last_graph_info(self):
+        B, n, has, gen = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+        self._ck(lib().tzr_last_graph_info(self._h, C.byref(B), C.byref(n), C.byref(has), C.byref(gen)))
+        return dict(B=B.value, n=n.value, has_graph=bool(has.value), generation=int(gen.value))
 
     # -- stages
     def graph_build(self, src, dst, beta):
@@ -477,3 +498,28 @@ class Context:
 
 def rotation_from_solution_record(rec) -> np.ndarray:
     return np.asarray(rec["rotation"]).reshape(3, 3).T.copy()
+
+
+def solve_batch_multi(src_list, dst_list, params: Params, devices=None):
+    """tzr_solve_batch_multi: one host call, the batch sharded over several GPUs inside the library (no torchrun).
+    src_list/dst_list: sequences of (N_b,3) float64 arrays.  Returns (solutions structured array, list of cliques)."""
+    B = len(src_list)
+    srcs = [_pts(a) for a in src_list]
+    dsts = [_pts(a) for a in dst_list]
+    n = np.array([a.shape[0] for a in srcs], dtype=np.int32)
+    max_n = int(n.max())
+    sp = (C.POINTER(C.c_double) * B)(*[_p(a, C.c_double) for a in srcs])
+    dp_ = (C.POINTER(C.c_double) * B)(*[_p(a, C.c_double) for a in dsts])
+    sols = (Solution * B)()
+    clq = np.zeros((B, max_n), dtype=np.int32)
+    if devices is None:
+        dev_p, n_dev = None, 0
+    else:
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        dev_p, n_dev = _p(dev, C.c_int32), int(dev.size)
+    rc = lib().tzr_solve_batch_multi(dev_p, n_dev, C.byref(params), B, _p(n, C.c_int32), sp, dp_, sols,
+                                     _p(clq, C.c_int32), max_n)
+    if rc != 0:
+        raise TzrError(f"tzr_solve_batch_multi: {lib().tzr_status_string(rc).decode()}")
+    out = np.frombuffer(bytes(sols), dtype=SOLUTION_DTYPE).copy()
+    return out, [clq[b, :out[b]["clique_size"]].copy() for b in range(B)]

@@ -4,7 +4,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tzr_internal.cuh"
@@ -25,7 +28,7 @@ struct tzr_ctx {
   uint32_t flags = 0;
   int num_sms = 148;
   // device buffers (grow-only)
-  DevBuf src, dst, sf, df, pk, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
+  DevBuf src, dst, sf, df, pk, opnd, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
       centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx, m_in, m_scratch, m_out, cert;
   // pinned host staging
   void* h_pin = nullptr;
@@ -36,8 +39,12 @@ struct tzr_ctx {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start | prep | graph tiles | clique (incl. degrees) | rot+trans
   std::vector<cudaEvent_t> graph_ev;  // pairs around every graph-kernel launch of the last call (roofline timing)
   int graph_ev_used = 0;
-  std::vector<cudaEvent_t> stage_ev;  // 5 per chunk of the last pipelined call (stage timing is summed over chunks)
-  int stage_chunks = 0;
+  std::vector<cudaEvent_t> stage_ev;  // 5 per chunk; [stage_first, stage_chunks) belong to the last pipelined call
+  int stage_chunks = 0, stage_first = 0, graph_first = 0;
+  bool stage_log = false;  // keep the events of every call since the last tzr_ctx_stage_log_read (bench.py: no sync per step)
+  int stage_log_calls = 0;
+  uint64_t generation = 0;   // bumped by every call that rebuilds or invalidates the retained graph (ctx->last)
+  bool last_has_graph = false;  // false: the last solve ran with inlier selection NONE (no graph was built)
   // chunked batches run on two lanes: the issue-bound graph kernels queue back to back on the low-priority gstream,
   // the latency-/HBM-bound degree, clique and rotation kernels of the previous chunk run on the high-priority hstream
   // and slot into the SMs as graph CTAs retire
@@ -109,6 +116,10 @@ int effective_mode(const tzr_params& p) {
 int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool complete_graph = false) {
   if (B <= 0 || n <= 0) return TZR_ERR_INVALID_ARG;
   if (n > kMaxN) return TZR_ERR_TOO_LARGE;
+  // the workspace is about to be re-used (and possibly re-allocated): the retained graph of the previous call is gone
+  ctx->have_last = false;
+  ctx->last_has_graph = false;
+  ++ctx->generation;
   Batch bt{};
   bt.B = B;
   bt.n = n;
@@ -124,6 +135,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   ENS(sf, Bn * sizeof(float4));
   ENS(df, Bn * sizeof(float4));
   ENS(pk, (size_t)B * 6 * npad128(n) * sizeof(float));
+  ENS(opnd, tc_operand_bytes(B, n));
   ENS(gc, (size_t)B * sizeof(GraphConsts));
   ENS(adj, Bn * pitch64(n) * sizeof(uint64_t));
   ENS(deg, Bn * sizeof(int32_t));
@@ -180,6 +192,7 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   bt.sf = (float4*)ctx->sf.p;
   bt.df = (float4*)ctx->df.p;
   bt.pk = (float*)ctx->pk.p;
+  bt.opnd = (float*)ctx->opnd.p;
   bt.gc = (GraphConsts*)ctx->gc.p;
   bt.adj = (uint64_t*)ctx->adj.p;
   bt.deg = (int32_t*)ctx->deg.p;
@@ -248,6 +261,7 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
   s.sf = bt.sf + o * n;
   s.df = bt.df + o * n;
   s.pk = bt.pk + o * 6 * (size_t)npad128(bt.n);
+  s.opnd = bt.opnd + tc_operand_bytes(b0, bt.n) / sizeof(float);
   s.gc = bt.gc + o;
   s.adj = bt.adj + o * n * pitch64(bt.n);
   s.deg = bt.deg + o * n;
@@ -374,7 +388,7 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
         ctx->graph_ev.push_back(e);
       }
       cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used], sg);
-      launch_graph(sb, sg);
+      launch_graph(sb, sg, ctx->num_sms);
       cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used + 1], sg);
       ctx->graph_ev_used += 2;
       if (sg != st) {  // two lanes (never combined with L2 sub-chunking: gch == B there)
@@ -405,8 +419,13 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
 int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<int>& bounds,
                 const cudaEvent_t* ready) {
   const int n_chunks = (int)bounds.size() - 1;
-  ctx->graph_ev_used = 0;
-  while ((int)ctx->stage_ev.size() < 5 * n_chunks) {
+  if (!ctx->stage_log) {
+    ctx->graph_ev_used = 0;
+    ctx->stage_chunks = 0;
+  }
+  ctx->stage_first = ctx->stage_chunks;
+  ctx->graph_first = ctx->graph_ev_used;
+  while ((int)ctx->stage_ev.size() < 5 * (ctx->stage_first + n_chunks)) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return TZR_ERR_CUDA;
     ctx->stage_ev.push_back(e);
@@ -430,7 +449,7 @@ int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<
       if (cudaStreamWaitEvent(sg, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
     }
     Batch sb = (n_chunks > 1) ? sub_batch(bt, b0, Bc) : bt;
-    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * c, st, sg, lanes ? ctx->gdone_ev[c] : nullptr);
+    int rc = run_pipeline(ctx, sb, p, ctx->stage_ev.data() + 5 * (ctx->stage_first + c), st, sg, lanes ? ctx->gdone_ev[c] : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) bt = sb;  // keep fields filled in by run_pipeline (beta, scale_mode, ...)
   }
@@ -440,9 +459,11 @@ int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<
     if (cudaEventRecord(ctx->join_ev2, ctx->gstream) != cudaSuccess) return TZR_ERR_CUDA;
     if (cudaStreamWaitEvent(ctx->stream, ctx->join_ev2, 0) != cudaSuccess) return TZR_ERR_CUDA;
   }
-  ctx->stage_chunks = n_chunks;
+  ctx->stage_chunks = ctx->stage_first + n_chunks;
+  if (ctx->stage_log) ++ctx->stage_log_calls;
   ctx->last = bt;
   ctx->have_last = true;
+  ctx->last_has_graph = effective_mode(p) != 3;  // NONE: populateVertices is never called (registration.cc:607-650)
   return TZR_OK;
 }
 
@@ -525,7 +546,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   if (!ctx) return TZR_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->pk, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
+  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->pk, &ctx->opnd, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->tstart, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
@@ -613,7 +634,7 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, d
   CK(cudaMemcpyAsync((void*)bt.dst, dst, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
   if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 16 * sizeof(unsigned long long), st);
   launch_prep(bt, st);
-  launch_graph(bt, st);
+  launch_graph(bt, st, ctx->num_sms);
   launch_degree(bt, st);
   ctx->launches += 3;
   rc = check_launch(ctx, "graph build");
@@ -627,6 +648,7 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, d
   if (n_edges) *n_edges = (int64_t)(e2 / 2);
   ctx->last = bt;
   ctx->have_last = true;
+  ctx->last_has_graph = true;
   return TZR_OK;
 }
 
@@ -982,12 +1004,26 @@ int tzr_last_graph(tzr_ctx* ctx, int b, uint64_t* adj_bits, int32_t* degree) {
   cudaSetDevice(ctx->device);
   const Batch& bt = ctx->last;
   const int n = bt.n;
+  if (!ctx->last_has_graph) {  // inlier selection NONE: the reference never populates the graph -> no edges
+    if (adj_bits) memset(adj_bits, 0, (size_t)n * words64(n) * 8);
+    if (degree) memset(degree, 0, (size_t)n * 4);
+    return TZR_OK;
+  }
   cudaStream_t st = ctx->stream;
   if (adj_bits)
     CK(cudaMemcpy2DAsync(adj_bits, (size_t)words64(n) * 8, bt.adj + (size_t)b * n * pitch64(n), (size_t)pitch64(n) * 8,
                          (size_t)words64(n) * 8, n, cudaMemcpyDeviceToHost, st));
   if (degree) CK(cudaMemcpyAsync(degree, bt.deg + (size_t)b * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return TZR_OK;
+}
+
+int tzr_last_graph_info(const tzr_ctx* ctx, int32_t* B, int32_t* n, int32_t* has_graph, uint64_t* generation) {
+  if (!ctx) return TZR_ERR_INVALID_ARG;
+  if (B) *B = ctx->have_last ? ctx->last.B : 0;
+  if (n) *n = ctx->have_last ? ctx->last.n : 0;
+  if (has_graph) *has_graph = (ctx->have_last && ctx->last_has_graph) ? 1 : 0;
+  if (generation) *generation = ctx->generation;
   return TZR_OK;
 }
 
@@ -1161,30 +1197,127 @@ int tzr_feature_nn(tzr_ctx* ctx, const float* query, int nq, const float* db, in
   return TZR_OK;
 }
 
-int tzr_last_stage_ms(tzr_ctx* ctx, double* prep_ms, double* graph_ms, double* clique_ms, double* rot_trans_ms) {
-  if (!ctx || !ctx->have_last) return TZR_ERR_INVALID_ARG;
-  double acc[4] = {0, 0, 0, 0};
-  for (int c = 0; c < ctx->stage_chunks; ++c)
+static int sum_stage_events(tzr_ctx* ctx, int c0, int c1, int g0, int g1, double acc[4]) {
+  for (int i = 0; i < 4; ++i) acc[i] = 0;
+  for (int c = c0; c < c1; ++c)
     for (int i = 0; i < 4; ++i) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, ctx->stage_ev[5 * c + i], ctx->stage_ev[5 * c + i + 1]) != cudaSuccess)
         return TZR_ERR_CUDA;
       acc[i] += ms;
     }
-  // graph = the graph kernel launches alone; the interleaved degree launches are booked under "clique"
+  // graph = the graph kernel launches alone (operand tiles + tensor-core kernel + strip kernel); the interleaved degree
+  // launches are booked under "clique"
   double g = 0;
-  for (int k = 0; k + 1 < ctx->graph_ev_used; k += 2) {
+  for (int k = g0; k + 1 < g1; k += 2) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->graph_ev[k], ctx->graph_ev[k + 1]) != cudaSuccess) return TZR_ERR_CUDA;
     g += ms;
   }
-  if (ctx->graph_ev_used > 0) {
+  if (g1 > g0) {
     acc[2] += acc[1] - g;
     acc[1] = g;
   }
+  return TZR_OK;
+}
+
+int tzr_last_stage_ms(tzr_ctx* ctx, double* prep_ms, double* graph_ms, double* clique_ms, double* rot_trans_ms) {
+  if (!ctx || !ctx->have_last) return TZR_ERR_INVALID_ARG;
+  double acc[4];
+  const int rc = sum_stage_events(ctx, ctx->stage_first, ctx->stage_chunks, ctx->graph_first, ctx->graph_ev_used, acc);
+  if (rc) return rc;
   double* outs[4] = {prep_ms, graph_ms, clique_ms, rot_trans_ms};
   for (int i = 0; i < 4; ++i)
     if (outs[i]) *outs[i] = acc[i];
+  return TZR_OK;
+}
+
+int tzr_ctx_stage_log(tzr_ctx* ctx, int enable) {
+  if (!ctx) return TZR_ERR_INVALID_ARG;
+  ctx->stage_log = enable != 0;
+  ctx->stage_chunks = ctx->stage_first = 0;
+  ctx->graph_ev_used = ctx->graph_first = 0;
+  ctx->stage_log_calls = 0;
+  return TZR_OK;
+}
+
+int tzr_ctx_stage_log_read(tzr_ctx* ctx, double* sums_ms4, int32_t* n_calls) {
+  if (!ctx || !sums_ms4) return TZR_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int rc = sum_stage_events(ctx, 0, ctx->stage_chunks, 0, ctx->graph_ev_used, sums_ms4);
+  if (rc) return rc;
+  if (n_calls) *n_calls = ctx->stage_log_calls;
+  ctx->stage_chunks = ctx->stage_first = 0;
+  ctx->graph_ev_used = ctx->graph_first = 0;
+  ctx->stage_log_calls = 0;
+  return TZR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU fan-out inside the library: one context + one host thread per device, contiguous shards balanced by
+// sum n_b^2 (the graph stage dominates), no collective.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DevicePool {
+  std::mutex mu;
+  std::map<int, tzr_ctx*> ctxs;
+  ~DevicePool() {
+    for (auto& kv : ctxs) tzr_ctx_destroy(kv.second);
+  }
+};
+DevicePool& device_pool() {
+  static DevicePool pool;
+  return pool;
+}
+}  // namespace
+
+int tzr_solve_batch_multi(const int32_t* devices, int n_devices, const tzr_params* params, int B, const int32_t* n,
+                          const double* const* src, const double* const* dst, tzr_solution* solutions,
+                          int32_t* cliques, int max_n) {
+  if (!params || !n || !src || !dst || !solutions || B <= 0) return TZR_ERR_INVALID_ARG;
+  std::vector<int> devs;
+  if (!devices || n_devices <= 0) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return TZR_ERR_NO_DEVICE;
+    for (int d = 0; d < count; ++d) devs.push_back(d);
+  } else {
+    devs.assign(devices, devices + n_devices);
+  }
+  DevicePool& pool = device_pool();
+  std::lock_guard<std::mutex> lock(pool.mu);
+  for (int d : devs)
+    if (!pool.ctxs.count(d)) {
+      tzr_ctx* c = nullptr;
+      const int rc = tzr_ctx_create(d, &c);
+      if (rc) return rc;
+      pool.ctxs[d] = c;
+    }
+  const int G = std::min<int>((int)devs.size(), B);
+  // contiguous shards with balanced sum n^2
+  std::vector<double> cum(B + 1, 0.0);
+  for (int b = 0; b < B; ++b) cum[b + 1] = cum[b] + (double)n[b] * (double)n[b];
+  std::vector<int> cut(G + 1, 0);
+  cut[G] = B;
+  for (int g = 1; g < G; ++g) {
+    const double target = cum[B] * g / G;
+    int b = cut[g - 1] + 1;  // at least one problem per shard
+    while (b < B - (G - g) && cum[b] < target) ++b;
+    cut[g] = b;
+  }
+  std::vector<int> rcs(G, TZR_OK);
+  std::vector<std::thread> threads;
+  for (int g = 0; g < G; ++g) {
+    threads.emplace_back([&, g] {
+      const int b0 = cut[g], Bg = cut[g + 1] - cut[g];
+      if (Bg <= 0) return;
+      rcs[g] = tzr_solve_batch(pool.ctxs[devs[g]], params, Bg, n + b0, src + b0, dst + b0, solutions + b0,
+                               cliques ? cliques + (size_t)b0 * max_n : nullptr, max_n);
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rcs[g]) return rcs[g];
   return TZR_OK;
 }
 

@@ -24,30 +24,6 @@
 namespace tzr {
 
 // ------------------------------------------------------------------------------------------------
-// exact predicate (tim_norm_exact lives in tzr_internal.cuh): the reference's operation sequence in IEEE
-// double, no contraction
-// ------------------------------------------------------------------------------------------------
-// Deliberately NOT inlined: the exact path runs for ~1e-4 of the pairs; keeping its two DSQRT expansions out
-// of the unrolled sweep keeps the hot loop small enough for the instruction cache.
-__device__ __noinline__ bool edge_exact(const double* __restrict__ src, const double* __restrict__ dst, int i,
-                                        int j, double beta) {
-  const double d1 = tim_norm_exact(src, i, j);
-  const double d2 = tim_norm_exact(dst, i, j);
-  return fabs(__dsub_rn(d1, d2)) <= beta;  // (v1_dist - v2_dist).abs() <= beta   registration.cc:442
-}
-
-// Unknown-scale predicate (TLSScaleSolver, registration.cc:410-425 + :86): the pair is an inlier iff
-// | d2/d1 - s_hat | <= beta * (1/d1), with s_hat the TLS scale estimate.
-__device__ __noinline__ bool edge_exact_scale(const double* __restrict__ src, const double* __restrict__ dst, int i,
-                                              int j, double beta, double s_hat) {
-  const double d1 = tim_norm_exact(src, i, j);
-  const double d2 = tim_norm_exact(dst, i, j);
-  const double ratio = __ddiv_rn(d2, d1);
-  const double alpha = __dmul_rn(beta, __ddiv_rn(1.0, d1));
-  return fabs(__dsub_rn(ratio, s_hat)) <= alpha;
-}
-
-// ------------------------------------------------------------------------------------------------
 // prep: bounding boxes, centred float copies, filter constants.  One CTA per problem.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_min(double v) {
@@ -145,6 +121,33 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     gc.b1 = (use64 || !(gam1 > 0)) ? -1.0f : (float)(gam1 * dn);
     gc.b2 = use64 ? __int_as_float(0x7f800000) : (float)(gam2 * up);
     gc.use_fp64 = use64;
+    gc.s_hat = s_hat;
+    // ---- tensor-core filter constants (graph_tc.cu; derivation in DESIGN.md §3.1).  a' = |ds|^2 and b' = |dd|^2 come
+    // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb; the kernel forms d' = (a'-b')^2 - beta^2 (sqrt a' +
+    // sqrt b')^2 in FP32 and decides by its sign unless |d'| <= theta or a'b' <= prisk.
+    {
+      double Ds2 = 0, Dd2 = 0;  // largest possible squared distance inside each (scaled) cloud
+      for (int k = 0; k < 3; ++k) {
+        const double es = (mx[k] - mn[k]) * s_hat, ed = mx[3 + k] - mn[3 + k];
+        Ds2 += es * es;
+        Dd2 += ed * ed;
+      }
+      const double Ds = sqrt(Ds2), Dd = sqrt(Dd2);
+      const double ea = kTcKappa * u32 * Ds2, eb = kTcKappa * u32 * Dd2;
+      const double dl = 32.0 * kTcKappa * u32 * fmax(Ds, Dd);  // g-space margin: |g' - g| <= dl once a' >= Amin, b' >= Bmin
+      const double Amin = (2.0 * ea / dl) * (2.0 * ea / dl), Bmin = (2.0 * eb / dl) * (2.0 * eb / dl);
+      const double ra = sqrt(Amin + ea) + beta + 2.0 * dl, rb = sqrt(Bmin + eb) + beta + 2.0 * dl;
+      const double Ub = ra * ra + eb, Ua = rb * rb + ea;
+      const double prisk = fmax(Amin * Ub, Bmin * Ua) * (1.0 + 1e-6);
+      const double Wmax = (Ds + Dd) * (Ds + Dd) * (1.0 + 1e-3) + 4.0 * (ea + eb);
+      const double theta = Wmax * (dl * (2.0 * beta + dl) + 8.0 * u32 * ((beta + dl) * (beta + dl) + beta * beta));
+      const bool ok = !use64 && (bt.flags_dbg & 512u) == 0 && beta > 4.0 * dl && Ds > 0 && Dd > 0 && Ds < 1e4 &&
+                      Dd < 1e4 && isfinite(theta) && isfinite(prisk) && beta * beta > 1e-30;
+      gc.use_tc = ok ? 1 : 0;
+      gc.tc_beta2 = (float)(beta * beta);
+      gc.tc_theta = (float)(theta * up);
+      gc.tc_prisk = fmaxf((float)(prisk * up), 1e-30f);
+    }
     bt.gc[b] = gc;
     bt.n_edges2[b] = 0ull;
   }
@@ -218,6 +221,7 @@ __device__ __forceinline__ PairEval classify(const float4 is, const float4 id, c
   return e;
 }
 
+#ifdef TZR_AB_KERNELS  // superseded designs, kept for A/B runs only (make AB=1)
 template <bool kVerify>
 __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) {
   const int b = blockIdx.y;
@@ -366,6 +370,8 @@ __global__ void __launch_bounds__(kGraphThreads, 5) graph_tile_kernel(Batch bt) 
   }
 }
 
+#endif  // TZR_AB_KERNELS
+
 // ------------------------------------------------------------------------------------------------
 // graph strip kernel (default): same sweep as graph_tile_kernel, but every WARP is independent — it owns 32 rows
 // and walks up to kStripBlocks consecutive 128-column blocks, keeps its 32 row points in a private shared-memory
@@ -400,6 +406,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   return x;
 }
 
+#ifdef TZR_AB_KERNELS
 template <bool kVerify, int kMinBlocks>
 __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip_kernel(Batch bt) {
   const int b = blockIdx.y;
@@ -539,6 +546,8 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip_kernel(
   }
 }
 
+#endif  // TZR_AB_KERNELS
+
 // ------------------------------------------------------------------------------------------------
 // graph strip kernel, packed-FP32 variant (default): identical decomposition and outputs as graph_strip_kernel,
 // but the twelve FP32 operations per pair run as sm_100 packed instructions (FADD2 / FMUL2 / FFMA2 via
@@ -605,6 +614,7 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel
   __shared__ __align__(16) uint32_t s_rw[kTile][4];
 
   const GraphConsts* gcp = bt.gc + b;
+  if (bt.tc_active && gcp->use_tc) return;  // built by graph_tc_kernel
   const float b1 = gcp->b1, b2 = gcp->b2;
   const double beta = gcp->beta;
   const bool scale_mode = bt.scale_mode != 0;
@@ -803,19 +813,27 @@ __global__ void __launch_bounds__(256) degree_kernel(Batch bt) {
 
 void launch_prep(const Batch& bt, cudaStream_t st) { prep_kernel<<<bt.B, 256, 0, st>>>(bt); }
 
-void launch_graph(const Batch& bt, cudaStream_t st) {
+void launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
+  Batch bt = bt0;
+  // default: tensor-core kernel for every problem prep_kernel marked use_tc, CUDA-core strip kernel for the rest
+  // (ill-conditioned filter, non-finite input); the A/B flags below run the CUDA-core kernels on everything
+  bt.tc_active = (bt.flags_dbg & (8u | 16u | 32u | 64u | 128u | 256u | 512u)) ? 0 : 1;
+  if (bt.tc_active) launch_graph_tc(bt, st, num_sms);
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)bt.B);
-  if (bt.flags_dbg & 8u) {  // previous design (one CTA per 128x128 tile, staged through shared memory): A/B only
+#ifdef TZR_AB_KERNELS
+  if (bt.flags_dbg & 8u) {  // first design (one CTA per 128x128 tile, staged through shared memory): A/B only
     if (bt.flags_dbg & 2u)
       graph_tile_kernel<true><<<grid, kGraphThreads, 0, st>>>(bt);
     else
       graph_tile_kernel<false><<<grid, kGraphThreads, 0, st>>>(bt);
     return;
   }
+#endif
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
   if (bt.flags_dbg & 2u)
     graph_strip2_kernel<true, 5, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+#ifdef TZR_AB_KERNELS
   else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
     graph_strip_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 32u)  // occupancy A/B: 5 CTAs/SM (96 registers)
@@ -824,9 +842,10 @@ void launch_graph(const Batch& bt, cudaStream_t st) {
     graph_strip_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 128u)  // packed kernel at 6 CTAs/SM
     graph_strip2_kernel<false, 6, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+#endif
   else if (bt.flags_dbg & 256u)  // degrees by the separate degree kernel (A/B against the fused default)
     graph_strip2_kernel<false, 8, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else  // default: packed FP32x2 strip kernel, 8 CTAs/SM, degrees fused
+  else  // packed FP32x2 strip kernel, 8 CTAs/SM, degrees fused
     graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
 }
 

@@ -26,6 +26,8 @@ constexpr int kGraphThreads = 128;  // 4 warps, each owns a 32x128 sub-tile (4 p
 constexpr int kHeurRoots = 4;       // heuristic start vertices per problem (top degrees); a global-peeling
                                     // second chance in the peel kernel covers the cases they all miss
 constexpr int kMatchMaxDim = 128;   // feature dimension limit of the matcher's NN kernel (FPFH: 33)
+constexpr double kTcKappa = 4.0;    // bound on the tensor-core Gram error |a' - a| in units of 2^-24 * D^2 (D = largest distance
+                                    // inside the cloud); measured with csrc/tc_probe (profiles/), x4 safety
 constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memory clique kernels
 
 // Per-problem constants of the FP32 filter (see graph_build.cu).
@@ -36,11 +38,18 @@ struct GraphConsts {
   int pad;
   double beta;    // 2*noise_bound*sqrt(cbar2)
   double cs[3], cd[3];  // centres subtracted before the float conversion
+  double s_hat;   // scale applied to the centred source copies (1 unless estimate_scaling)
+  // tensor-core filter (graph_tc.cu): d = (a-b)^2 - beta^2 (sqrt(a)+sqrt(b))^2 from the Gram-form squared norms
+  int use_tc;     // 1: this problem goes through graph_tc_kernel, 0: through the CUDA-core strip kernel
+  float tc_beta2; // beta^2
+  float tc_theta; // |d| <= theta          : undecided -> exact FP64 re-check
+  float tc_prisk; // a*b <= prisk (or < 0) : undecided -> exact FP64 re-check (tiny / cancelled squared norms)
 };
 
 // Everything the device kernels need to know about one batch (passed by value).
 struct Batch {
   int B;          // problems
+  int tc_active;  // 1: problems with gc.use_tc are built by graph_tc_kernel and skipped by the CUDA-core strip kernel
   int scale_mode; // 1: estimate_scaling=true (TLSScaleSolver predicate, scale from sol[b].scale)
   int n;          // correspondences per problem (uniform inside a device batch)
   double beta;    // 2*noise_bound*sqrt(cbar2)  (registration.cc:438)
@@ -48,6 +57,8 @@ struct Batch {
   const double* dst;  // B*n*3
   float4* sf;     // B*n centred float copies (w unused)
   float4* df;
+  float* opnd;    // B * ceil(n/128) * 2 roles * 2 clouds * 6 planes * 128 rows * 4: tf32-split MMA operand tiles of the
+                  // tensor-core graph kernel (graph_tc.cu), written by tc_prep_kernel
   float* pk;      // B*6*npad128(n): the same centred floats, pair-interleaved per 128-column block for the packed
                   // FP32x2 graph kernel (arrays sx,sy,sz,dx,dy,dz; element of point j at blk*128 + k*64 + lane*2 + half)
   GraphConsts* gc;        // B
@@ -103,9 +114,33 @@ __device__ __forceinline__ double tim_norm_exact(const double* __restrict__ p, i
   return __dsqrt_rn(s);
 }
 
+// exact predicate: the reference's operation sequence in IEEE double, no contraction (registration.cc:427-443).
+// Deliberately NOT inlined: it runs for ~1e-4 of the pairs; keeping its two DSQRT expansions out of the unrolled
+// sweeps keeps the hot loops small enough for the instruction cache.
+static __device__ __noinline__ bool edge_exact(const double* __restrict__ src, const double* __restrict__ dst, int i,
+                                               int j, double beta) {
+  const double d1 = tim_norm_exact(src, i, j);
+  const double d2 = tim_norm_exact(dst, i, j);
+  return fabs(__dsub_rn(d1, d2)) <= beta;  // (v1_dist - v2_dist).abs() <= beta   registration.cc:442
+}
+
+// Unknown-scale predicate (TLSScaleSolver, registration.cc:410-425 + :86): the pair is an inlier iff
+// | d2/d1 - s_hat | <= beta * (1/d1), with s_hat the TLS scale estimate.
+static __device__ __noinline__ bool edge_exact_scale(const double* __restrict__ src, const double* __restrict__ dst,
+                                                     int i, int j, double beta, double s_hat) {
+  const double d1 = tim_norm_exact(src, i, j);
+  const double d2 = tim_norm_exact(dst, i, j);
+  const double ratio = __ddiv_rn(d2, d1);
+  const double alpha = __dmul_rn(beta, __ddiv_rn(1.0, d1));
+  return fabs(__dsub_rn(ratio, s_hat)) <= alpha;
+}
+
 // kernels (defined in the .cu files) -------------------------------------------------------------
 void launch_prep(const Batch& bt, cudaStream_t st);
-void launch_graph(const Batch& bt, cudaStream_t st);
+void launch_graph(const Batch& bt, cudaStream_t st, int num_sms);
+// graph_tc.cu: tensor-core path (operand tiles + tcgen05 kernel) for the problems prep_kernel marked use_tc
+int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms);
+size_t tc_operand_bytes(int B, int n);
 // bitset_only: the adjacency did not come from launch_graph (tzr_max_clique on a caller's bitset): always popcount
 void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only = false);
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);

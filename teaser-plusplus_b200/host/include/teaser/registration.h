@@ -250,6 +250,13 @@ class RobustRegistrationSolver {
   Params getParams() { return params_; }
 
   // B200 extras (not in the reference)
+  // Many independent problems in one call: the batch is cut into shards and every shard is solved on its own GPU
+  // (tzr_solve_batch_multi: one context + host thread per device inside the library, no collective) with this
+  // solver's Params.  devices empty = every visible device.  cliques (optional) receives the sorted max-clique index
+  // sets.  The per-problem getters of this object are not touched.
+  std::vector<RegistrationSolution> solveBatch(
+      const std::vector<Mat3X>& src, const std::vector<Mat3X>& dst, std::vector<std::vector<int>>* cliques = nullptr,
+      const std::vector<int>& devices = {});
   bool isMaxCliqueProvenOptimal() const { return clique_proven_; }
   long long getNumInlierGraphEdges() const { return n_edges_; }
   int getGNCRotationIterations() const { return gnc_iterations_; }
@@ -277,6 +284,7 @@ class RobustRegistrationSolver {
   int gnc_iterations_ = 0;
   bool clique_proven_ = false;
   long long n_edges_ = 0;
+  unsigned long long graph_generation_ = 0;  // tzr_last_graph_info generation right after this solver's solve()
 };
 
 // Context shared by all façade objects of the calling thread (a tzr_ctx is not thread-safe).

@@ -112,6 +112,21 @@ PYBIND11_MODULE(_teaserpp, m) {
              py::gil_scoped_release release;  // the reference holds the GIL; nothing here touches Python
              return s.solve(a, b);
            })
+      .def("solve_batch",
+           [](Solver& s, const std::vector<ArrD>& src, const std::vector<ArrD>& dst, const std::vector<int>& devices) {
+             // B200 extra: many independent problems in one call, sharded over the GPUs of the node inside the library
+             std::vector<teaser::Mat3X> a, b;
+             for (const auto& x : src) a.push_back(to_mat3x(x));
+             for (const auto& x : dst) b.push_back(to_mat3x(x));
+             std::vector<std::vector<int>> cliques;
+             std::vector<teaser::RegistrationSolution> sols;
+             {
+               py::gil_scoped_release release;
+               sols = s.solveBatch(a, b, &cliques, devices);
+             }
+             return py::make_tuple(sols, cliques);
+           },
+           py::arg("src"), py::arg("dst"), py::arg("devices") = std::vector<int>{})
       .def_property_readonly("solution", &Solver::getSolution)
       .def("getSolution", &Solver::getSolution)
       .def_property_readonly("gnc_rotation_cost_at_termination", &Solver::getGNCRotationCostAtTermination)

@@ -294,6 +294,11 @@ RegistrationSolution RobustRegistrationSolver::solve(const Mat3X& src, const Mat
   last_dst_ = dst;
   have_graph_ = have_tims_ = false;
   solved_ = true;
+  {
+    uint64_t gen = 0;
+    tzr_last_graph_info(ctx, nullptr, nullptr, nullptr, &gen);
+    graph_generation_ = gen;
+  }
   solution_.valid = s.valid != 0;
   solution_.scale = s.scale;
   for (int k = 0; k < 3; ++k) solution_.translation(k) = s.translation[k];
@@ -382,19 +387,31 @@ RegistrationSolution RobustRegistrationSolver::solve_decoupled(const Mat3X& src,
     for (Eigen::Index i = 0; i < src.cols(); ++i) max_clique_.push_back(static_cast<int>(i));
   }
   const size_t m = max_clique_.size();
-  pruned_src_tims_.resize(3, m);
-  pruned_dst_tims_.resize(3, m);
-  src_tims_map_rotation_.resize(2, m);
-  dst_tims_map_rotation_.resize(2, m);
-  for (size_t i = 0; i < m; ++i) {
-    const int root = max_clique_[i];
-    const int leaf = (i + 1 != m) ? max_clique_[i + 1] : max_clique_[0];
-    for (int r = 0; r < 3; ++r) {
-      pruned_src_tims_(r, i) = src(r, leaf) - src(r, root);
-      pruned_dst_tims_(r, i) = (dst(r, leaf) - dst(r, root)) * (1 / solution_.scale);
+  if (params_.rotation_tim_graph == INLIER_GRAPH_FORMULATION::COMPLETE) {  // registration.cc:681-694
+    Mat3X si(3, m), di(3, m);
+    for (size_t i = 0; i < m; ++i)
+      for (int r = 0; r < 3; ++r) {
+        si(r, i) = src(r, max_clique_[i]);
+        di(r, i) = dst(r, max_clique_[i]);
+      }
+    pruned_dst_tims_ = computeTIMs(di, &dst_tims_map_rotation_);
+    pruned_src_tims_ = computeTIMs(si, &src_tims_map_rotation_);
+    pruned_dst_tims_ *= (1 / solution_.scale);
+  } else {
+    pruned_src_tims_.resize(3, m);
+    pruned_dst_tims_.resize(3, m);
+    src_tims_map_rotation_.resize(2, m);
+    dst_tims_map_rotation_.resize(2, m);
+    for (size_t i = 0; i < m; ++i) {
+      const int root = max_clique_[i];
+      const int leaf = (i + 1 != m) ? max_clique_[i + 1] : max_clique_[0];
+      for (int r = 0; r < 3; ++r) {
+        pruned_src_tims_(r, i) = src(r, leaf) - src(r, root);
+        pruned_dst_tims_(r, i) = (dst(r, leaf) - dst(r, root)) * (1 / solution_.scale);
+      }
+      src_tims_map_rotation_(0, i) = dst_tims_map_rotation_(0, i) = leaf;
+      src_tims_map_rotation_(1, i) = dst_tims_map_rotation_(1, i) = root;
     }
-    src_tims_map_rotation_(0, i) = dst_tims_map_rotation_(0, i) = leaf;
-    src_tims_map_rotation_(1, i) = dst_tims_map_rotation_(1, i) = root;
   }
   // fresh noise bound every call (the reference mutates it in place)
   auto rp = rotation_solver_->getParams();
@@ -447,6 +464,25 @@ void RobustRegistrationSolver::materialise_graph() {
   if (have_graph_ || !solved_) return;
   const int n = static_cast<int>(last_src_.cols());
   tzr_ctx* ctx = b200_context();
+  // The graph lives in the per-thread context until someone asks for it.  If another solver (or a stage call such as
+  // MaxCliqueSolver::findMaxClique) has used the context since this object's solve(), the retained graph is not ours
+  // any more: rebuild it by solving the stored inputs again.
+  int32_t gB = 0, gn = 0, has = 0;
+  uint64_t gen = 0;
+  tzr_last_graph_info(ctx, &gB, &gn, &has, &gen);
+  if (gen != graph_generation_ || gn != n || gB != 1) {
+    tzr_params p = to_c(params_);
+    tzr_solution s;
+    int rc = tzr_solve(ctx, &p, last_src_.data(), last_dst_.data(), n, &s, nullptr, nullptr, nullptr);
+    if (rc != TZR_OK) fail("getInlierGraph (re-solve)", rc, ctx);
+    tzr_last_graph_info(ctx, &gB, &gn, &has, &gen);
+    graph_generation_ = gen;
+  }
+  if (!has) {  // inlier selection NONE: populateVertices is never called, the reference's graph stays empty
+    inlier_graph_.clear();
+    have_graph_ = true;
+    return;
+  }
   const int W = tzr_words_per_row(n);
   std::vector<uint64_t> bits(static_cast<size_t>(n) * W);
   std::vector<int32_t> deg(n);
@@ -468,6 +504,43 @@ void RobustRegistrationSolver::materialise_graph() {
   }
   inlier_graph_.setAdjList(std::move(adj), twice / 2);
   have_graph_ = true;
+}
+
+std::vector<RegistrationSolution> RobustRegistrationSolver::solveBatch(
+    const std::vector<Mat3X>& src, const std::vector<Mat3X>& dst, std::vector<std::vector<int>>* cliques,
+    const std::vector<int>& devices) {
+  if (src.size() != dst.size()) throw std::invalid_argument("teaser: solveBatch needs as many src as dst clouds");
+  const int B = static_cast<int>(src.size());
+  std::vector<RegistrationSolution> out(B);
+  if (B == 0) return out;
+  std::vector<int32_t> n(B), dev(devices.begin(), devices.end());
+  std::vector<const double*> sp(B), dp(B);
+  int max_n = 0;
+  for (int b = 0; b < B; ++b) {
+    if (src[b].cols() != dst[b].cols()) throw std::invalid_argument("teaser: src and dst must have the same number of columns");
+    n[b] = static_cast<int32_t>(src[b].cols());
+    sp[b] = src[b].data();
+    dp[b] = dst[b].data();
+    max_n = std::max(max_n, static_cast<int>(n[b]));
+  }
+  std::vector<tzr_solution> sols(B);
+  std::vector<int32_t> clq(cliques ? static_cast<size_t>(B) * max_n : 0);
+  tzr_params p = to_c(params_);
+  int rc = tzr_solve_batch_multi(dev.empty() ? nullptr : dev.data(), static_cast<int>(dev.size()), &p, B, n.data(),
+                                 sp.data(), dp.data(), sols.data(), cliques ? clq.data() : nullptr, max_n);
+  if (rc != TZR_OK) fail("RobustRegistrationSolver::solveBatch", rc, nullptr);
+  if (cliques) cliques->assign(B, {});
+  for (int b = 0; b < B; ++b) {
+    out[b].valid = sols[b].valid != 0;
+    out[b].scale = sols[b].scale;
+    for (int k = 0; k < 3; ++k) out[b].translation(k) = sols[b].translation[k];
+    std::memcpy(out[b].rotation.data(), sols[b].rotation, sizeof(sols[b].rotation));
+    if (cliques) {
+      const int m = std::max(0, sols[b].clique_size);
+      (*cliques)[b].assign(clq.begin() + static_cast<size_t>(b) * max_n, clq.begin() + static_cast<size_t>(b) * max_n + m);
+    }
+  }
+  return out;
 }
 
 void RobustRegistrationSolver::materialise_tims() {

@@ -11,5 +11,6 @@ done
 cp "$REF/examples/example_data/bun_zipper_res3.ply" "$HERE/"
 cp "$REF/test/teaser/data/cube.ply" "$HERE/"
 cp "$REF/test/teaser/data/bunny.pcd" "$REF/test/teaser/data/bunny_fpfh.csv" "$HERE/"
+cp "$REF/test/teaser/data/canstick.ply" "$REF/test/teaser/data/matcher-test-object-1.ply" "$REF/test/teaser/data/matcher-test-scene-1.ply" "$REF/test/teaser/data/matcher-test-matches-1.csv" "$HERE/"
 cp -r "$REF/test/teaser/data/certification_small_instances" "$REF/test/teaser/data/certification_large_instances" "$HERE/"
 chmod -R u+w "$HERE"

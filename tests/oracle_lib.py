@@ -102,6 +102,8 @@ def lib():
     i64p = C.POINTER(C.c_int64)
     u64p = C.POINTER(C.c_uint64)
     L.orc_num_threads.restype = C.c_int
+    L.orc_set_num_threads.argtypes = [C.c_int]
+    L.orc_set_num_threads.restype = None
     L.orc_compute_tims.argtypes = [dp, C.c_int64, dp, i32p]
     L.orc_scale_inliers_selector.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_double, dp, u8p]
     L.orc_tls_scale_solver.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_double, dp, u8p]

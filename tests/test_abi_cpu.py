@@ -41,7 +41,7 @@ def test_params_defaults_match_reference():
     assert p.kcore_heuristic_threshold == 0.5 and p.use_max_clique == 1 and p.max_clique_exact_solution == 1
     assert p.max_clique_time_limit == 3600
     assert capi.lib().tzr_words_per_row(5000) == 79
-    assert capi.lib().tzr_abi_version() == 1
+    assert capi.lib().tzr_abi_version() == 2
 
 
 def test_struct_layouts_agree():
