@@ -271,7 +271,8 @@ int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx);
 /* Number of pairs of the most recent graph build that needed the exact FP64 re-check. */
 int64_t tzr_ctx_filter_rechecks(tzr_ctx* ctx);
 /* Debug counters of the most recent call (flag bit 2 set): [0] filter mismatches, [1] filter re-checks, [2] clique
- * search nodes, [3] reduce rounds, [4] vertices scanned by reduce rounds, [5] colourings, [6] vertices coloured. */
+ * search nodes, [3] reduce rounds, [4] vertices scanned by reduce rounds, [5] colourings, [6] vertices coloured,
+ * [7] problems whose graph was built by the tensor-core kernel. */
 int tzr_ctx_debug_counters(tzr_ctx* ctx, int64_t* out16);
 
 #ifdef __cplusplus

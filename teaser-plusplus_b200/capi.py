@@ -232,7 +232,7 @@ class Context:
         self._ck(lib().tzr_ctx_debug_counters(self._h, _p(out, C.c_int64)))
         return dict(filter_mismatches=int(out[0]), filter_rechecks=int(out[1]), clique_nodes=int(out[2]),
                     reduce_rounds=int(out[3]), reduce_vertices=int(out[4]), colourings=int(out[5]),
-                    coloured_vertices=int(out[6]))
+                    coloured_vertices=int(out[6]), tc_problems=int(out[7]))
 
     def kernel_launches(self) -> int:
         return int(lib().tzr_ctx_kernel_launches(self._h))

@@ -329,7 +329,8 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
   if (mode == 0 && p.max_clique_time_limit > 0 && p.max_clique_time_limit < 1e7)
     bt.budget_ns = (unsigned long long)(p.max_clique_time_limit * 1e9);
   // unknown scale (Params default): TLS over the K TIM ratios first (registration.cc:603 -> :410-425)
-  constexpr int kScaleSmallN = 1500;  // single-CTA bitonic sort + sequential sweep below, sort/scan pipeline above
+  constexpr int kScaleSmallN = 256;  // single-CTA bitonic sort + sequential one-thread sweep below (bit-exact vs the
+                                     // reference's order; ~1 ms at 256), radix-sort + parallel-scan pipeline above
   bt.scale_mode = p.estimate_scaling ? 1 : 0;
   double *scx = nullptr, *scr = nullptr, *sckey = nullptr;
   int32_t* scidx = nullptr;

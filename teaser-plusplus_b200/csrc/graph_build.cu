@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
       const bool ok = !use64 && (bt.flags_dbg & 512u) == 0 && beta > 4.0 * dl && Ds > 0 && Dd > 0 && Ds < 1e4 &&
                       Dd < 1e4 && isfinite(theta) && isfinite(prisk) && beta * beta > 1e-30;
       gc.use_tc = ok ? 1 : 0;
+      if (ok && bt.rechecks) atomicAdd(bt.mismatches + 7, 1ull);  // debug counter 7: problems on the tensor-core path
       gc.tc_beta2 = (float)(beta * beta);
       gc.tc_theta = (float)(theta * up);
       gc.tc_prisk = fmaxf((float)(prisk * up), 1e-30f);

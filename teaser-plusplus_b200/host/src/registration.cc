@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -306,6 +307,12 @@ RegistrationSolution RobustRegistrationSolver::solve(const Mat3X& src, const Mat
   gnc_cost_ = s.gnc_cost;
   gnc_iterations_ = s.gnc_iterations;
   clique_proven_ = s.clique_proven_optimal != 0;
+  if (!clique_proven_ && s.valid && to_c(params_).inlier_selection_mode == 0 && params_.use_max_clique &&
+      params_.max_clique_exact_solution)
+    // the exact search ran into max_clique_time_limit or its stack budget: the clique is the best one found, not
+    // proven maximum (the reference's PMC prints its own time-limit notice in that situation)
+    std::fprintf(stderr, "[teaser-b200] warning: maximum clique search incomplete (time/stack budget); returning the "
+                         "best clique found (%d vertices)\n", s.clique_size);
   n_edges_ = s.n_edges;
   const size_t m = static_cast<size_t>(std::max(0, s.clique_size));
   max_clique_.assign(clique.begin(), clique.begin() + m);
