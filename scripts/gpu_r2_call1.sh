@@ -2,6 +2,8 @@
 # round 2, GPU call 1: tensor-core probe, graph parity through the new kernel, first timings of every config
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
+# incremental: rebuilds only what is older than its sources (guards against a snapshot taken mid-build)
+(make -s -j16 -C teaser-plusplus_b200/csrc && make -s -C teaser-plusplus_b200/csrc tc_probe && make -s -C teaser-plusplus_b200/host && make -s -C oracle) > gpurun_out/build.log 2>&1; echo "build rc=$?"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 240 teaser-plusplus_b200/csrc/tc_probe > gpurun_out/tc_probe.log 2>&1; echo "probe rc=$?" >> gpurun_out/tc_probe.log
 tail -60 gpurun_out/tc_probe.log

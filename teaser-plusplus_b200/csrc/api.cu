@@ -225,6 +225,18 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   bt.mismatches = (unsigned long long*)ctx->dbg.p;
   bt.rechecks = (ctx->flags & 4u) ? (unsigned long long*)ctx->dbg.p + 1 : nullptr;
   bt.flags_dbg = ctx->flags;
+  {
+    static const double kappa_env = [] {
+      const char* e = std::getenv("TZR_TC_KAPPA");
+      return e ? std::atof(e) : 0.0;
+    }();
+    static const int swap_env = [] {
+      const char* e = std::getenv("TZR_TC_SWAP");
+      return e ? std::atoi(e) : 0;
+    }();
+    bt.tc_kappa = kappa_env;
+    bt.tc_desc_swap = swap_env;
+  }
   bt.budget_ns = 0ull;
   *out = bt;
   return TZR_OK;

@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     gc.use_fp64 = use64;
     gc.s_hat = s_hat;
     // ---- tensor-core filter constants (graph_tc.cu; derivation in DESIGN.md §3.1).  a' = |ds|^2 and b' = |dd|^2 come
-    // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb; the kernel forms d' = (a'-b')^2 - beta^2 (sqrt a' +
-    // sqrt b')^2 in FP32 and decides by its sign unless |d'| <= theta or a'b' <= prisk.
+    // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb (E = ea + eb); the kernel forms t' = a'-b' and
+    // d' = t'^2 - beta^2 (sqrt a' + sqrt b')^2 in FP32 and decides by the sign of d' unless
+    //   d'^2 <= t'^2 (k1 + k2 t'^2)   [ <= ( 7.5 E |t'| + 24 u t'^2 )^2 ... the band ]   or  a' < ga  or  b' < gb.
     {
       double Ds2 = 0, Dd2 = 0;  // largest possible squared distance inside each (scaled) cloud
       for (int k = 0; k < 3; ++k) {
@@ -132,22 +133,19 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
         Ds2 += es * es;
         Dd2 += ed * ed;
       }
-      const double Ds = sqrt(Ds2), Dd = sqrt(Dd2);
-      const double ea = kTcKappa * u32 * Ds2, eb = kTcKappa * u32 * Dd2;
-      const double dl = 32.0 * kTcKappa * u32 * fmax(Ds, Dd);  // g-space margin: |g' - g| <= dl once a' >= Amin, b' >= Bmin
-      const double Amin = (2.0 * ea / dl) * (2.0 * ea / dl), Bmin = (2.0 * eb / dl) * (2.0 * eb / dl);
-      const double ra = sqrt(Amin + ea) + beta + 2.0 * dl, rb = sqrt(Bmin + eb) + beta + 2.0 * dl;
-      const double Ub = ra * ra + eb, Ua = rb * rb + ea;
-      const double prisk = fmax(Amin * Ub, Bmin * Ua) * (1.0 + 1e-6);
-      const double Wmax = (Ds + Dd) * (Ds + Dd) * (1.0 + 1e-3) + 4.0 * (ea + eb);
-      const double theta = Wmax * (dl * (2.0 * beta + dl) + 8.0 * u32 * ((beta + dl) * (beta + dl) + beta * beta));
-      const bool ok = !use64 && (bt.flags_dbg & 512u) == 0 && beta > 4.0 * dl && Ds > 0 && Dd > 0 && Ds < 1e4 &&
-                      Dd < 1e4 && isfinite(theta) && isfinite(prisk) && beta * beta > 1e-30;
+      const double kappa = bt.tc_kappa > 0 ? bt.tc_kappa : kTcKappa;
+      const double ea = kappa * u32 * Ds2, eb = kappa * u32 * Dd2, E = ea + eb;
+      const double ct = 7.5 * E, cf = 24.0 * u32;
+      const double ga = (2.25 * beta * ea / E) * (2.25 * beta * ea / E), gb = (2.25 * beta * eb / E) * (2.25 * beta * eb / E);
+      const bool ok = !use64 && (bt.flags_dbg & 512u) == 0 && Ds2 > 0 && Dd2 > 0 && Ds2 < 1e8 && Dd2 < 1e8 &&
+                      E <= beta * beta / 8.0 && beta * beta > 1e-30 && isfinite(E);
       gc.use_tc = ok ? 1 : 0;
-      if (ok && bt.rechecks) atomicAdd(bt.mismatches + 7, 1ull);  // debug counter 7: problems on the tensor-core path
       gc.tc_beta2 = (float)(beta * beta);
-      gc.tc_theta = (float)(theta * up);
-      gc.tc_prisk = fmaxf((float)(prisk * up), 1e-30f);
+      gc.tc_k1 = (float)(2.0 * ct * ct * up);
+      gc.tc_k2 = (float)(2.0 * cf * cf * up);
+      gc.tc_ga = fmaxf((float)(ga * up), 1e-36f);
+      gc.tc_gb = fmaxf((float)(gb * up), 1e-36f);
+      if (ok && bt.rechecks) atomicAdd(bt.mismatches + 7, 1ull);  // debug counter 7: problems on the tensor-core path
     }
     bt.gc[b] = gc;
     bt.n_edges2[b] = 0ull;

@@ -11,19 +11,21 @@
 // is a K = 3 (+2 for the norms) contraction.  Every centred coordinate (and every norm) is split into three tf32
 // pieces h + m + l (11 significant bits each, so the split carries 33 bits of the FP64 value), and the products
 // hh', hm', mh', mm', hl', lh' plus the six norm pieces are laid out as a K = 24 tf32 GEMM (three K = 8 tcgen05.mma
-// steps per cloud): one 128x128 tile of a and of b lands in tensor memory per 6 MMAs, issued by one thread.  The
+// steps per cloud): one 128x64 tile of a and of b lands in tensor memory per 6 MMAs, issued by one thread.  The
 // operand tiles (tc_prep_kernel writes them once per problem in the exact shared-memory image the MMA descriptor
-// wants: no-swizzle K-major planes) are staged by the TMA engine (cp.async.bulk -> UBLKCP) into a double-buffered
-// shared-memory ring, completion on mbarriers.
+// wants: no-swizzle K-major planes) are staged by the TMA engine (cp.async.bulk -> UBLKCP) into a shared-memory ring,
+// completion on mbarriers; the accumulators are double-buffered in TMEM so the MMAs of tile t+1 run under the
+// epilogue of tile t.
 //
-// Epilogue (8 warps, tcgen05.ld 32 lanes x 32 columns): with t = a-b, s = a+b, q = sqrt(ab) (one MUFU per pair)
+// Epilogue (8 warps, tcgen05.ld 32 lanes x 16 columns): with t = a-b, s = a+b, q = sqrt(ab) (one MUFU per pair)
 //     d = t^2 - beta^2 (s + 2q) = (sqrt a + sqrt b)^2 (g^2 - beta^2),      g = |sqrt a - sqrt b|
 // so the pair is an edge iff d <= 0.  This form is well conditioned (both sides are equal at the threshold, so the
 // FP32 evaluation error is a few ulp of beta^2 (sqrt a + sqrt b)^2, no cancellation of D^2-sized terms against
-// beta^2).  The sign bit of d is shifted straight into the row word (no compare, no ballot); min |d| and min ab over
-// the 32 pairs of a thread are tracked with two 3-input FMNMX, and only if min|d| <= theta or min ab <= prisk
-// (prep_kernel) the warp revisits its chunk and re-evaluates the flagged pairs with the reference's
-// exact FP64 sequence.  6 issue slots + 1 MUFU per pair instead of ~20 + 2.
+// beta^2).  The sign bit of d is shifted straight into the row word (no compare, no ballot); whether any of the
+// thread's 32 pairs falls into the error band of the tensor-core norms (d^2 <= t^2 (k1 + k2 t^2), or a tiny a / b;
+// prep_kernel) is tracked with three 3-input FMNMX, and only then the warp revisits its chunk (re-read
+// from TMEM) and re-evaluates the flagged pairs with the reference's exact FP64 sequence.  7 issue slots + 1 MUFU per
+// pair instead of ~20 + 2.
 // Output (packed symmetric bitset, fused degrees) is bit-identical to graph_build.cu's and to the oracle's.
 #include "tc_ptx.cuh"
 #include "tzr_internal.cuh"
@@ -32,18 +34,24 @@ namespace tzr {
 
 using namespace tc;
 
-constexpr int kTcEpiWarps = 8;                       // warp w: TMEM lanes 32*(w&3).., columns 64*(w>>2)..
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);   // + 1 producer warp (TMA + MMA issue by one elected lane)
-constexpr int kTcPlaneBytes = 128 * 16;              // 128 rows x 4 tf32
-constexpr int kTcCloudBytes = 6 * kTcPlaneBytes;     // 6 planes = K 24
-constexpr int kTcRoleBytes = 2 * kTcCloudBytes;      // src + dst
-constexpr int kTcBlockBytes = 2 * kTcRoleBytes;      // A role + B role of one 128-point block
-constexpr int kTcSmemBytes = 4 * kTcRoleBytes + 256; // A x2, B x2, barriers
+constexpr int kTcEpiWarps = 8;                        // warp w: TMEM lanes 32*(w&3).., columns 32*(w>>2)..
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);    // + 1 producer warp (TMA + MMA issue by one elected lane)
+constexpr int kTcN = 64;                              // columns of one tile (MMA N)
+constexpr int kTcPlaneA = 128 * 16;                   // A role: 128 rows x 4 tf32 per plane
+constexpr int kTcPlaneB = kTcN * 16;                  // B role: 64 rows x 4 tf32 per plane
+constexpr int kTcCloudA = 6 * kTcPlaneA, kTcCloudB = 6 * kTcPlaneB;   // 6 planes = K 24
+constexpr int kTcTileA = 2 * kTcCloudA;               // src + dst: 24 KB per 128-row block
+constexpr int kTcTileB = 2 * kTcCloudB;               // 12 KB per 64-column block
+constexpr int kTcBStages = 4;
+constexpr int kTcSmemBytes = 2 * kTcTileA + kTcBStages * kTcTileB + 256;
 
-size_t tc_operand_bytes(int B, int n) { return (size_t)B * ((n + kTile - 1) / kTile) * kTcBlockBytes; }
+__host__ __device__ inline size_t tc_a_bytes(int n) { return (size_t)((n + 127) / 128) * kTcTileA; }
+__host__ __device__ inline size_t tc_b_bytes(int n) { return (size_t)((n + kTcN - 1) / kTcN) * kTcTileB; }
+size_t tc_operand_bytes(int B, int n) { return (size_t)B * (tc_a_bytes(n) + tc_b_bytes(n)); }
 
 // ------------------------------------------------------------------------------------------------
-// operand tiles.  One thread per point; block (blk, b).
+// operand tiles.  One thread per point; block (blk, b) covers 128 points.  Per problem: all A-role blocks (128 rows
+// each), then all B-role blocks (64 rows each).
 // A-role plane p of a cloud holds [c_x, c_y, c_z, w] per row with (piece, w) = (h,N0) (h,N1) (m,N2) (m,1) (h,1) (l,1);
 // B-role: -2 x pieces (h,m,h,m,l,h) with w = 1,1,1,N0,N1,N2, so that sum_k A_ik B_jk = N_i + N_j - 2 (hh'+hm'+mh'+mm'+hl'+lh').
 // ------------------------------------------------------------------------------------------------
@@ -60,9 +68,13 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
   const int b = blockIdx.y, blk = blockIdx.x, r = threadIdx.x;
   const GraphConsts* gc = bt.gc + b;
   if (!gc->use_tc) return;
-  const int n = bt.n, nt = (n + kTile - 1) / kTile;
+  const int n = bt.n;
   const int j = blk * kTile + r;
-  float4* out = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bt.opnd) + ((size_t)b * nt + blk) * kTcBlockBytes);
+  uint8_t* base = reinterpret_cast<uint8_t*>(bt.opnd) + (size_t)b * (tc_a_bytes(n) + tc_b_bytes(n));
+  float4* outA = reinterpret_cast<float4*>(base + (size_t)blk * kTcTileA);
+  float4* outB = reinterpret_cast<float4*>(base + tc_a_bytes(n) + (size_t)(2 * blk + (r >> 6)) * kTcTileB);
+  const int rb = r & 63;
+  const bool haveB = 2 * blk + (r >> 6) < (n + kTcN - 1) / kTcN;  // the last 128-block may own only one 64-block
   const double* src = bt.src + (size_t)b * n * 3;
   const double* dst = bt.dst + (size_t)b * n * 3;
 #pragma unroll
@@ -80,8 +92,8 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
     }
     float N0, N1, N2;
     split3(nrm, N0, N1, N2);
-    float4* A = out + cloud * (kTcCloudBytes / 16);
-    float4* Bq = out + (kTcRoleBytes / 16) + cloud * (kTcCloudBytes / 16);
+    float4* A = outA + cloud * (kTcCloudA / 16);
+    float4* Bq = outB + cloud * (kTcCloudB / 16);
     const float one = j < n ? 1.f : 0.f;  // rows past n: all-zero operands (finite results, masked later)
     A[0 * 128 + r] = make_float4(c[0][0], c[1][0], c[2][0], N0);
     A[1 * 128 + r] = make_float4(c[0][0], c[1][0], c[2][0], N1);
@@ -89,30 +101,34 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
     A[3 * 128 + r] = make_float4(c[0][1], c[1][1], c[2][1], one);
     A[4 * 128 + r] = make_float4(c[0][0], c[1][0], c[2][0], one);
     A[5 * 128 + r] = make_float4(c[0][2], c[1][2], c[2][2], one);
-    Bq[0 * 128 + r] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], one);
-    Bq[1 * 128 + r] = make_float4(-2.f * c[0][1], -2.f * c[1][1], -2.f * c[2][1], one);
-    Bq[2 * 128 + r] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], one);
-    Bq[3 * 128 + r] = make_float4(-2.f * c[0][1], -2.f * c[1][1], -2.f * c[2][1], N0);
-    Bq[4 * 128 + r] = make_float4(-2.f * c[0][2], -2.f * c[1][2], -2.f * c[2][2], N1);
-    Bq[5 * 128 + r] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], N2);
+    if (haveB) {
+      Bq[0 * kTcN + rb] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], one);
+      Bq[1 * kTcN + rb] = make_float4(-2.f * c[0][1], -2.f * c[1][1], -2.f * c[2][1], one);
+      Bq[2 * kTcN + rb] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], one);
+      Bq[3 * kTcN + rb] = make_float4(-2.f * c[0][1], -2.f * c[1][1], -2.f * c[2][1], N0);
+      Bq[4 * kTcN + rb] = make_float4(-2.f * c[0][2], -2.f * c[1][2], -2.f * c[2][2], N1);
+      Bq[5 * kTcN + rb] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], N2);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// tile schedule: a work item is a strip = (problem b, row block I, column blocks J0 .. J0+S-1 of the upper triangle).
-// CTA c walks items c, c + gridDim.x, ...; the producer lane and the epilogue warps iterate the same sequence.
+// tile schedule: a work item is a strip = (problem b, row block I of 128, S consecutive 64-column blocks J of the
+// upper triangle, J >= 2I).  CTA c walks items c, c + gridDim.x, ...; the producer lane and the epilogue warps iterate
+// the same sequence.
 // ------------------------------------------------------------------------------------------------
 struct TileIter {
-  int item, step, total, spp, S, nt;
+  int item, step, total, spp, S, nt, nt64;
   int b, I, J, J1;
   bool first;
-  __device__ __forceinline__ void init(int start, int step_, int total_, int spp_, int S_, int nt_) {
+  __device__ __forceinline__ void init(int start, int step_, int total_, int spp_, int S_, int n) {
     item = start - step_;
     step = step_;
     total = total_;
     spp = spp_;
     S = S_;
-    nt = nt_;
+    nt = (n + kTile - 1) / kTile;
+    nt64 = (n + kTcN - 1) / kTcN;
     b = I = 0;
     J = J1 = 0;
     first = false;
@@ -129,13 +145,13 @@ struct TileIter {
     int p = item - b * spp;
     I = 0;
     while (true) {
-      const int ng = (nt - I + S - 1) / S;
+      const int ng = (nt64 - 2 * I + S - 1) / S;
       if (p < ng) break;
       p -= ng;
       ++I;
     }
-    J = I + p * S;
-    J1 = min(nt, J + S);
+    J = 2 * I + p * S;
+    J1 = min(nt64, J + S);
     first = true;
     return true;
   }
@@ -143,9 +159,9 @@ struct TileIter {
 };
 
 __host__ __device__ inline int tc_strips_per_problem(int n, int S) {
-  const int nt = (n + kTile - 1) / kTile;
+  const int nt = (n + kTile - 1) / kTile, nt64 = (n + kTcN - 1) / kTcN;
   int total = 0;
-  for (int I = 0; I < nt; ++I) total += (nt - I + S - 1) / S;
+  for (int I = 0; I < nt; ++I) total += (nt64 - 2 * I + S - 1) / S;
   return total;
 }
 
@@ -184,21 +200,67 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
-__device__ __forceinline__ float sqrt_approx_tc(float x) {  // MUFU.SQRT, max relative error 2^-23 (part of theta)
+__device__ __forceinline__ float sqrt_approx_tc(float x) {  // MUFU.SQRT, max relative error 2^-23 (inside the 24 u term)
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// d and p = a*b for two pairs; shared by the sweep and the (rare) revisit so both see identical values
-__device__ __forceinline__ void tc_pair2(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, f32x2 two, f32x2 nbeta2,
-                                         float& d0, float& d1, float& p0, float& p1) {
+struct TcConsts {
+  f32x2 two, nbeta2, nk1, nk2;
+  float ga, gb;
+};
+
+// d = t^2 - beta^2 (sqrt a + sqrt b)^2 and the band test value r = d^2 - t^2 (k1 + k2 t^2) for two pairs; shared by
+// the sweep and the (rare) revisit so both see identical values.  nk1 / nk2 hold -k1 / -k2.
+__device__ __forceinline__ void tc_pair2(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, const TcConsts& k,
+                                         float& d0, float& d1, float& r0, float& r1) {
   const f32x2 A = pk2(a0, a1), B = pk2(b0, b1);
   const f32x2 t = sub2(A, B), s = add2(A, B), p = mul2(A, B);
+  float p0, p1;
   upk2(p, p0, p1);
   const f32x2 q = pk2f(sqrt_approx_tc(p0), sqrt_approx_tc(p1));
-  const f32x2 w = fma2(q, two, s), t2 = mul2(t, t), d = fma2(w, nbeta2, t2);
+  const f32x2 w = fma2(q, k.two, s), t2 = mul2(t, t), d = fma2(w, k.nbeta2, t2);
+  const f32x2 nz = fma2(t2, k.nk2, k.nk1), ny = mul2(t2, nz), r = fma2(d, d, ny);
   upk2(d, d0, d1);
+  upk2(r, r0, r1);
+}
+
+// 16 pairs (columns c0 .. c0+15 of the warp's 32): shifts their sign bits into `word` (call with the upper half first)
+// and folds the band / guard minima
+__device__ __forceinline__ void tc_sweep16(uint32_t ta, uint32_t tb, const TcConsts& k, uint32_t& word, float& m1,
+                                           float& ma, float& mb) {
+  uint32_t ra[16], rb[16];
+  tmem_ld16(ta, ra);
+  tmem_ld16(tb, rb);
+  tmem_wait_ld();
+#pragma unroll
+  for (int c = 14; c >= 0; c -= 2) {
+    float d0, d1, r0, r1;
+    tc_pair2(ra[c], ra[c + 1], rb[c], rb[c + 1], k, d0, d1, r0, r1);
+    word = __funnelshift_l(__float_as_uint(d1), word, 1);
+    word = __funnelshift_l(__float_as_uint(d0), word, 1);
+    m1 = fminf(m1, fminf(r0, r1));
+    ma = fminf(ma, fminf(__uint_as_float(ra[c]), __uint_as_float(ra[c + 1])));
+    mb = fminf(mb, fminf(__uint_as_float(rb[c]), __uint_as_float(rb[c + 1])));
+  }
+}
+
+// the same 16 pairs again: which of them are undecided
+__device__ __forceinline__ uint32_t tc_flags16(uint32_t ta, uint32_t tb, const TcConsts& k) {
+  uint32_t ra[16], rb[16];
+  tmem_ld16(ta, ra);
+  tmem_ld16(tb, rb);
+  tmem_wait_ld();
+  uint32_t f = 0u;
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    float d0, d1, r0, r1;
+    tc_pair2(ra[c], ra[c + 1], rb[c], rb[c + 1], k, d0, d1, r0, r1);
+    if (!(r0 > 0.f) || !(__uint_as_float(ra[c]) > k.ga) || !(__uint_as_float(rb[c]) > k.gb)) f |= 1u << c;
+    if (!(r1 > 0.f) || !(__uint_as_float(ra[c + 1]) > k.ga) || !(__uint_as_float(rb[c + 1]) > k.gb)) f |= 2u << c;
+  }
+  return f;
 }
 
 // 32x32 bit transpose across the lanes of a warp (lane l passes row l, receives column l)
@@ -218,84 +280,108 @@ __device__ __forceinline__ uint32_t tc_transpose32(uint32_t x, int lane) {
 }
 
 // barrier slots in shared memory
-enum { kBarAFull0 = 0, kBarAFull1, kBarBFull0, kBarBFull1, kBarBEmpty0, kBarBEmpty1, kBarTmemFull, kBarTmemEmpty, kNumBars };
+enum {
+  kBarAFull = 0,                          // [2]  TMA -> MMA: A tile of the strip landed
+  kBarAEmpty = 2,                         // [2]  MMA commit -> TMA: the strip's A tile has been read for the last time
+  kBarBFull = 4,                          // [kTcBStages]  TMA -> MMA
+  kBarBEmpty = kBarBFull + kTcBStages,    // [kTcBStages]  MMA commit -> TMA: stage may be overwritten
+  kBarTFull = kBarBEmpty + kTcBStages,    // [2]  MMA commit -> epilogue: accumulator stage ready
+  kBarTEmpty = kBarTFull + 2,             // [2]  epilogue (8 arrivals) -> MMA: accumulator stage drained
+  kNumBars = kBarTEmpty + 2
+};
 
 template <bool kVerify>
 __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S, int spp, int total_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kTcRoleBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 4 * kTcRoleBytes + 8 * kNumBars);
-  const uint32_t sA0 = smem_u32(smem), sB0 = smem_u32(smem + 2 * kTcRoleBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcTileA + kTcBStages * kTcTileB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const uint32_t sA0 = smem_u32(smem), sB0 = smem_u32(smem + 2 * kTcTileA);
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = bt.n, nt = (n + kTile - 1) / kTile;
+  const int n = bt.n;
   if (tid == 0) {
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i == kBarTmemEmpty ? kTcEpiWarps : 1);
+    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i >= kBarTEmpty ? kTcEpiWarps : 1);
     mbar_fence_init();
   }
   if (warp == kTcEpiWarps) tmem_alloc<256>(smem_u32(tmem_slot));
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tbase = *tmem_slot;
+  const uint32_t tbase = *tmem_slot;  // accumulator stage s: a at columns 128 s .. +63, b at 128 s + 64 .. +63
 
   if (warp == kTcEpiWarps) {
-    // ================= producer: TMA loads one tile ahead, MMA issue =================
+    // ================= producer: TMA loads (kTcBStages - 1 tiles ahead), MMA issue =================
     if (lane == 0) {
       const uint8_t* opnd = reinterpret_cast<const uint8_t*>(bt.opnd);
+      const size_t per_problem = tc_a_bytes(n) + tc_b_bytes(n), a_bytes = tc_a_bytes(n);
       TileIter ld, mm;
-      ld.init(blockIdx.x, gridDim.x, total_items, spp, S, nt);
-      mm.init(blockIdx.x, gridDim.x, total_items, spp, S, nt);
+      ld.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
+      mm.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
       uint32_t n_loaded = 0, n_strips_loaded = 0, n_mma = 0, n_strips = 0, ap = 0;
-      auto issue_load = [&](const TileIter& t) {
-        const uint32_t st = n_loaded & 1u, use = n_loaded >> 1;
-        if (use > 0) mbar_wait(bar(kBarBEmpty0 + st), (use - 1) & 1u);  // MMAs that read this stage are complete
-        if (t.first) {
-          const uint32_t a = n_strips_loaded & 1u;
-          mbar_arrive_expect_tx(bar(kBarAFull0 + a), kTcRoleBytes);
-          bulk_g2s(sA0 + a * kTcRoleBytes, opnd + ((size_t)t.b * nt + t.I) * kTcBlockBytes, kTcRoleBytes, bar(kBarAFull0 + a));
-          ++n_strips_loaded;
-        }
-        mbar_arrive_expect_tx(bar(kBarBFull0 + st), kTcRoleBytes);
-        bulk_g2s(sB0 + st * kTcRoleBytes, opnd + ((size_t)t.b * nt + t.J) * kTcBlockBytes + kTcRoleBytes, kTcRoleBytes,
-                 bar(kBarBFull0 + st));
-        ++n_loaded;
-      };
       auto next_tc = [&](TileIter& t) {  // next tile of a problem that takes the tensor-core path
         while (t.next())
           if (bt.gc[t.b].use_tc) return true;
         return false;
       };
-      const uint32_t idesc = make_idesc_tf32(128, 128);
-      bool have_ld = next_tc(ld);
-      if (have_ld) issue_load(ld);
+      auto issue_load = [&](const TileIter& t) {
+        const uint32_t st = n_loaded % kTcBStages, use = n_loaded / kTcBStages;
+        if (use > 0) mbar_wait(bar(kBarBEmpty + st), (use - 1) & 1u);  // the MMAs that read this stage are complete
+        const uint8_t* pb = opnd + (size_t)t.b * per_problem;
+        if (t.first) {
+          // A buffer (strip index & 1): wait until the strip that used it two strips ago has been read completely
+          const uint32_t a = n_strips_loaded & 1u;
+          if (n_strips_loaded >= 2) mbar_wait(bar(kBarAEmpty + a), ((n_strips_loaded >> 1) - 1) & 1u);
+          mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
+          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
+          ++n_strips_loaded;
+        }
+        mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
+        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
+        ++n_loaded;
+      };
+      const uint32_t idesc = make_idesc_tf32(128, kTcN);
+      // The loads run ahead of the MMAs by at most kTcBStages - 1 tiles and at most one strip: this thread issues both,
+      // so a load may only wait for commits of MMAs that have ALREADY been issued (B stage of tile n_loaded - kTcBStages,
+      // A buffer of the strip before the previous one) — otherwise it would wait for itself.
+      bool pend = next_tc(ld);
+      auto can_load = [&]() {
+        return pend && (n_loaded - n_mma) < (uint32_t)(kTcBStages - 1) && (!ld.first || n_strips >= n_strips_loaded);
+      };
+      while (can_load()) {
+        issue_load(ld);
+        pend = next_tc(ld);
+      }
       while (next_tc(mm)) {
-        have_ld = have_ld && next_tc(ld);
-        if (have_ld) issue_load(ld);
-        const uint32_t st = n_mma & 1u, use = n_mma >> 1;
+        const uint32_t st = n_mma % kTcBStages, use = n_mma / kTcBStages;
+        const uint32_t ts = n_mma & 1u, tuse = n_mma >> 1;
         if (mm.first) {
           ap = n_strips & 1u;
-          mbar_wait(bar(kBarAFull0 + ap), (n_strips >> 1) & 1u);
+          mbar_wait(bar(kBarAFull + ap), (n_strips >> 1) & 1u);
           ++n_strips;
         }
-        mbar_wait(bar(kBarBFull0 + st), use & 1u);
-        if (n_mma > 0) mbar_wait(bar(kBarTmemEmpty), (n_mma - 1) & 1u);  // the epilogue has drained the previous tile
+        mbar_wait(bar(kBarBFull + st), use & 1u);
+        if (tuse > 0) mbar_wait(bar(kBarTEmpty + ts), (tuse - 1) & 1u);  // the epilogue has drained this accumulator stage
         fence_after_sync();
+        // K-major, no swizzle: leading byte offset = distance of the two 16-byte K-chunks (planes), stride byte offset
+        // = distance of consecutive 8-row groups (128 B)
 #pragma unroll
         for (int cloud = 0; cloud < 2; ++cloud)
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            const uint64_t da = make_smem_desc(sA0 + ap * kTcRoleBytes + cloud * kTcCloudBytes + s * 2 * kTcPlaneBytes,
-                                               kTcPlaneBytes, 128);
-            const uint64_t db = make_smem_desc(sB0 + st * kTcRoleBytes + cloud * kTcCloudBytes + s * 2 * kTcPlaneBytes,
-                                               kTcPlaneBytes, 128);
-            mma_tf32(tbase + 128u * cloud, da, db, idesc, s > 0);
+            const uint64_t da = make_smem_desc(sA0 + ap * kTcTileA + cloud * kTcCloudA + s * 2 * kTcPlaneA, kTcPlaneA, 128);
+            const uint64_t db = make_smem_desc(sB0 + st * kTcTileB + cloud * kTcCloudB + s * 2 * kTcPlaneB, kTcPlaneB, 128);
+            mma_tf32(tbase + 128u * ts + (uint32_t)kTcN * cloud, da, db, idesc, s > 0);
           }
-        mma_commit(bar(kBarBEmpty0 + st));
-        mma_commit(bar(kBarTmemFull));
+        mma_commit(bar(kBarBEmpty + st));
+        if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
+        mma_commit(bar(kBarTFull + ts));
         ++n_mma;
+        while (can_load()) {
+          issue_load(ld);
+          pend = next_tc(ld);
+        }
       }
     }
     __syncwarp();
@@ -304,108 +390,91 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     TileIter ti;
-    ti.init(blockIdx.x, gridDim.x, total_items, spp, S, nt);
+    ti.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
     uint32_t n_t = 0;
     int rdeg = 0;
     const int P32 = pitch32(n);
-    const f32x2 two = pk2f(2.f, 2.f);
+    TcConsts kc;
+    kc.two = pk2f(2.f, 2.f);
+    kc.nbeta2 = kc.nk1 = kc.nk2 = kc.two;
+    kc.ga = kc.gb = 0.f;
     while (ti.next()) {
       const GraphConsts* gcp = bt.gc + ti.b;
       if (!gcp->use_tc) continue;
       const int b = ti.b, I = ti.I, J = ti.J;
-      const float beta2 = gcp->tc_beta2, theta = gcp->tc_theta, prisk = gcp->tc_prisk;
-      const f32x2 nbeta2 = pk2f(-beta2, -beta2);
+      if (ti.first) {
+        kc.nbeta2 = pk2f(-gcp->tc_beta2, -gcp->tc_beta2);
+        kc.nk1 = pk2f(-gcp->tc_k1, -gcp->tc_k1);
+        kc.nk2 = pk2f(-gcp->tc_k2, -gcp->tc_k2);
+        kc.ga = gcp->tc_ga;
+        kc.gb = gcp->tc_gb;
+      }
       const int i = I * kTile + 32 * q + lane;
+      const int j0 = J * kTcN + 32 * h;
       uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * P32;
       int* degp = bt.deg + (size_t)b * n;
-      mbar_wait(bar(kBarTmemFull), n_t & 1u);
+      const uint32_t ts = n_t & 1u;
+      mbar_wait(bar(kBarTFull + ts), (n_t >> 1) & 1u);
       fence_after_sync();
-      uint32_t word0 = 0u, word1 = 0u;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = 64 * h + 32 * c;
-        const int j0 = J * kTile + col0;
-        uint32_t ra[32], rb[32];
-        tmem_ld32(tbase + lane_base + (uint32_t)col0, ra);
-        tmem_ld32(tbase + lane_base + 128u + (uint32_t)col0, rb);
-        tmem_wait_ld();
-        if (c == 1) {  // both chunks of this warp are in registers: hand the accumulator back to the MMA issuer
-          fence_before_sync();
-          if (lane == 0) mbar_arrive(bar(kBarTmemEmpty));
-        }
-        // ---- sweep: bit k of word = sign(d_k), i.e. pair (i, j0+k) classified as an edge
-        uint32_t word = 0u;
-        float m1 = __int_as_float(0x7f800000), m2 = __int_as_float(0x7f800000);
-#pragma unroll
-        for (int k = 30; k >= 0; k -= 2) {
-          float d0, d1, p0, p1;
-          tc_pair2(ra[k], ra[k + 1], rb[k], rb[k + 1], two, nbeta2, d0, d1, p0, p1);
-          word = __funnelshift_l(__float_as_uint(d1), word, 1);
-          word = __funnelshift_l(__float_as_uint(d0), word, 1);
-          m1 = fminf(m1, fminf(fabsf(d0), fabsf(d1)));
-          m2 = fminf(m2, fminf(p0, p1));
-        }
-        // validity of the pairs of this thread: columns < n, row < n, i != j
-        uint32_t vmask = j0 + 32 <= n ? 0xffffffffu : (j0 >= n ? 0u : ((1u << (n - j0)) - 1u));
-        if (i >= n) vmask = 0u;
-        if (i >= j0 && i < j0 + 32) vmask &= ~(1u << (i - j0));
-        const bool flagged = !(m1 > theta) || !(m2 > prisk);
-        if (kVerify || __any_sync(0xffffffffu, flagged && vmask != 0u)) {
-          // ---- rare: find the undecided pairs of this thread and re-evaluate them with the exact FP64 sequence
-          uint32_t fmask = 0u;
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            float d0, d1, p0, p1;
-            tc_pair2(ra[k], ra[k + 1], rb[k], rb[k + 1], two, nbeta2, d0, d1, p0, p1);
-            if (!(fabsf(d0) > theta) || !(p0 > prisk)) fmask |= 1u << k;
-            if (!(fabsf(d1) > theta) || !(p1 > prisk)) fmask |= 2u << k;
-          }
-          fmask &= vmask;
-          const double* src = bt.src + (size_t)b * n * 3;
-          const double* dst = bt.dst + (size_t)b * n * 3;
-          const double beta = gcp->beta;
-          const bool scale_mode = bt.scale_mode != 0;
-          const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
-          if (kVerify) {  // every DECIDED pair is re-evaluated exactly; disagreements are counted (must stay 0)
-            uint32_t vm = vmask & ~fmask;
-            int bad = 0;
-            while (vm) {
-              const int k = __ffs(vm) - 1;
-              vm &= vm - 1;
-              const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j0 + k, beta, s_hat) : edge_exact(src, dst, i, j0 + k, beta);
-              bad += (ex != (((word >> k) & 1u) != 0u));
-            }
-            if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
-          }
-          int nre = 0;
-          while (fmask) {
-            const int k = __ffs(fmask) - 1;
-            fmask &= fmask - 1;
+      const uint32_t ta = tbase + lane_base + 128u * ts + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
+      // ---- sweep: bit k of word = sign(d_k), i.e. pair (i, j0+k) classified as an edge
+      uint32_t word = 0u;
+      float m1 = __int_as_float(0x7f800000), ma = m1, mb = m1;
+      tc_sweep16(ta + 16u, tb + 16u, kc, word, m1, ma, mb);
+      tc_sweep16(ta, tb, kc, word, m1, ma, mb);
+      // validity of the pairs of this thread: columns < n, row < n, i != j
+      uint32_t vmask = j0 + 32 <= n ? 0xffffffffu : (j0 >= n ? 0u : ((1u << (n - j0)) - 1u));
+      if (i >= n) vmask = 0u;
+      if (i >= j0 && i < j0 + 32) vmask &= ~(1u << (i - j0));
+      const bool flagged = !(m1 > 0.f) || !(ma > kc.ga) || !(mb > kc.gb);
+      if (kVerify || __any_sync(0xffffffffu, flagged && vmask != 0u)) {
+        // ---- rare: find the undecided pairs of this thread and re-evaluate them with the exact FP64 sequence
+        uint32_t fmask = tc_flags16(ta, tb, kc) | (tc_flags16(ta + 16u, tb + 16u, kc) << 16);
+        fmask &= vmask;
+        const double* src = bt.src + (size_t)b * n * 3;
+        const double* dst = bt.dst + (size_t)b * n * 3;
+        const double beta = gcp->beta;
+        const bool scale_mode = bt.scale_mode != 0;
+        const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
+        if (kVerify) {  // every DECIDED pair is re-evaluated exactly; disagreements are counted (must stay 0)
+          uint32_t vm = vmask & ~fmask;
+          int bad = 0;
+          while (vm) {
+            const int k = __ffs(vm) - 1;
+            vm &= vm - 1;
             const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j0 + k, beta, s_hat) : edge_exact(src, dst, i, j0 + k, beta);
-            word = (word & ~(1u << k)) | ((ex ? 1u : 0u) << k);
-            ++nre;
+            bad += (ex != (((word >> k) & 1u) != 0u));
           }
-          if (bt.rechecks) {
-            nre = __reduce_add_sync(0xffffffffu, nre);
-            if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
-          }
+          if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
         }
-        word &= vmask;
-        if (c == 0)
-          word0 = word;
-        else
-          word1 = word;
-        rdeg += __popc(word);
-        if (I != J) {  // transposed half: lane l holds column j0+l over rows I*128 + 32q .. +31
-          const uint32_t colw = tc_transpose32(word, lane);
-          const int jc = j0 + lane;
-          if (jc < n) {
-            adj32[(size_t)jc * P32 + 4 * I + q] = colw;
-            if (colw) atomicAdd(degp + jc, __popc(colw));
-          }
+        int nre = 0;
+        while (fmask) {
+          const int k = __ffs(fmask) - 1;
+          fmask &= fmask - 1;
+          const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j0 + k, beta, s_hat) : edge_exact(src, dst, i, j0 + k, beta);
+          word = (word & ~(1u << k)) | ((ex ? 1u : 0u) << k);
+          ++nre;
+        }
+        if (bt.rechecks) {
+          nre = __reduce_add_sync(0xffffffffu, nre);
+          if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
         }
       }
-      if (i < n) *reinterpret_cast<uint2*>(adj32 + (size_t)i * P32 + 4 * J + 2 * h) = make_uint2(word0, word1);
+      // hand the accumulator stage back to the MMA issuer (all TMEM reads of this warp are complete)
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarTEmpty + ts));
+      word &= vmask;
+      rdeg += __popc(word);
+      if (i < n) adj32[(size_t)i * P32 + 2 * J + h] = word;
+      if ((J >> 1) != I) {  // transposed half: lane l holds column j0+l over rows I*128 + 32q .. +31
+        const uint32_t colw = tc_transpose32(word, lane);
+        const int jc = j0 + lane;
+        if (jc < n) {
+          adj32[(size_t)jc * P32 + 4 * I + q] = colw;
+          if (colw) atomicAdd(degp + jc, __popc(colw));
+        }
+      }
       if (ti.last_of_strip()) {
         if (i < n && rdeg) atomicAdd(degp + i, rdeg);
         rdeg = 0;
@@ -430,9 +499,9 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 pg((unsigned)nt, (unsigned)bt.B);
   tc_prep_kernel<<<pg, 128, 0, st>>>(bt);
-  // strip length: long strips amortise the A tile, short ones balance small batches
+  // strip length (in 64-column tiles): long strips amortise the A tile, short ones balance small batches
   const int ctas = 2 * num_sms;
-  int S = 8;
+  int S = 16;
   while (S > 1 && (long long)bt.B * tc_strips_per_problem(bt.n, S) < 4LL * ctas) S >>= 1;
   const int spp = tc_strips_per_problem(bt.n, S);
   const long long total = (long long)bt.B * spp;

@@ -26,7 +26,7 @@ constexpr int kGraphThreads = 128;  // 4 warps, each owns a 32x128 sub-tile (4 p
 constexpr int kHeurRoots = 4;       // heuristic start vertices per problem (top degrees); a global-peeling
                                     // second chance in the peel kernel covers the cases they all miss
 constexpr int kMatchMaxDim = 128;   // feature dimension limit of the matcher's NN kernel (FPFH: 33)
-constexpr double kTcKappa = 4.0;    // bound on the tensor-core Gram error |a' - a| in units of 2^-24 * D^2 (D = largest distance
+constexpr double kTcKappa = 12.0;   // bound on the tensor-core Gram error |a' - a| in units of 2^-24 * D^2 (D = largest distance
                                     // inside the cloud); measured with csrc/tc_probe (profiles/), x4 safety
 constexpr int kMaxN = 32768;        // per-problem size limit of the shared-memory clique kernels
 
@@ -42,13 +42,15 @@ struct GraphConsts {
   // tensor-core filter (graph_tc.cu): d = (a-b)^2 - beta^2 (sqrt(a)+sqrt(b))^2 from the Gram-form squared norms
   int use_tc;     // 1: this problem goes through graph_tc_kernel, 0: through the CUDA-core strip kernel
   float tc_beta2; // beta^2
-  float tc_theta; // |d| <= theta          : undecided -> exact FP64 re-check
-  float tc_prisk; // a*b <= prisk (or < 0) : undecided -> exact FP64 re-check (tiny / cancelled squared norms)
+  float tc_k1, tc_k2;  // d^2 <= t^2 (k1 + k2 t^2) : undecided -> exact FP64 re-check   (t = a - b)
+  float tc_ga, tc_gb;  // a < ga or b < gb         : undecided -> exact FP64 re-check (tiny / cancelled squared norms)
 };
 
 // Everything the device kernels need to know about one batch (passed by value).
 struct Batch {
   int B;          // problems
+  double tc_kappa; // bound on the tensor-core Gram error in units of 2^-24 D^2 (kTcKappa; env TZR_TC_KAPPA for experiments)
+  int tc_desc_swap; // debug (env TZR_TC_SWAP): exchange the leading/stride byte offsets of the MMA operand descriptors
   int tc_active;  // 1: problems with gc.use_tc are built by graph_tc_kernel and skipped by the CUDA-core strip kernel
   int scale_mode; // 1: estimate_scaling=true (TLSScaleSolver predicate, scale from sol[b].scale)
   int n;          // correspondences per problem (uniform inside a device batch)
