@@ -304,6 +304,7 @@ def main():
     sols = np.frombuffer(sol_d.cpu().numpy().tobytes(), dtype=capi.SOLUTION_DTYPE)
     clq = clq_d.cpu().numpy()
     n_ok = sum(int(np.array_equal(clq[b, :sols[b]["clique_size"]], inliers[b])) for b in range(B))
+    n_sub = sum(int(np.isin(inliers[b], clq[b, :sols[b]["clique_size"]]).all()) for b in range(B))
     # one untimed step with the debug counters on: exact re-checks of the graph filter, clique search nodes
     ctx.set_flags(base_flags | 4)
     step_dev()
@@ -439,9 +440,11 @@ def main():
             "counters": {"graph_exact_rechecks_per_problem": counters["filter_rechecks"] / B,
                          "clique_search_nodes_per_problem": counters["clique_nodes"] / B},
             "parity": {"timed_batch_clique_equals_planted_inliers": f"{n_ok}/{B}",
+                       "timed_batch_planted_inliers_subset_of_clique": f"{n_sub}/{B}",
                        "e2e_batch_clique_equals_planted_inliers": f"{e2e_ok}/{B}",
-                       "note": "ground-truth check; a planted set can be strictly inside the maximum clique when an "
-                               "outlier happens to be consistent with every inlier"},
+                       "note": "ground-truth check, not parity: with in-cube / permuted outliers some outliers are consistent "
+                               "with every inlier, so the maximum clique is a strict superset of the planted set (C3: 105 vs "
+                               "100); parity is vs_oracle below"},
         }
         if args.estimate_scaling:
             # the K-element TLS is "HBM-bound for real": sort traffic ~ 4 passes x 2K end points x 12 B.

@@ -28,7 +28,7 @@ struct tzr_ctx {
   uint32_t flags = 0;
   int num_sms = 148;
   // device buffers (grow-only)
-  DevBuf src, dst, sf, df, pk, opnd, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
+  DevBuf src, dst, sf, df, pk, opnd, tclist, gc, adj, deg, nedges, hclq, hsize, clq, L, alive, best_bits, alive_cnt, root_ctr, lock, flg, kfinal, tstart, stack, cv,
       centry, ps, pd, wgt, res, skey, sidx, sorted, rmask, tmask, sol, dbg, misc, sc_x, sc_r, sc_key, sc_idx, m_in, m_scratch, m_out, cert;
   // pinned host staging
   void* h_pin = nullptr;
@@ -136,6 +136,8 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   ENS(df, Bn * sizeof(float4));
   ENS(pk, (size_t)B * 6 * npad128(n) * sizeof(float));
   ENS(opnd, tc_operand_bytes(B, n));
+  bt.tc_list_cap = (unsigned int)tc_list_entries(B, n);
+  ENS(tclist, (size_t)bt.tc_list_cap * sizeof(uint2) + 256);
   ENS(gc, (size_t)B * sizeof(GraphConsts));
   ENS(adj, Bn * pitch64(n) * sizeof(uint64_t));
   ENS(deg, Bn * sizeof(int32_t));
@@ -193,6 +195,8 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   bt.df = (float4*)ctx->df.p;
   bt.pk = (float*)ctx->pk.p;
   bt.opnd = (float*)ctx->opnd.p;
+  bt.tc_list_count = (unsigned int*)ctx->tclist.p;
+  bt.tc_list = (uint2*)((char*)ctx->tclist.p + 256);
   bt.gc = (GraphConsts*)ctx->gc.p;
   bt.adj = (uint64_t*)ctx->adj.p;
   bt.deg = (int32_t*)ctx->deg.p;
@@ -401,7 +405,7 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
         ctx->graph_ev.push_back(e);
       }
       cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used], sg);
-      launch_graph(sb, sg, ctx->num_sms);
+      nl += launch_graph(sb, sg, ctx->num_sms) - 1;
       cudaEventRecord(ctx->graph_ev[ctx->graph_ev_used + 1], sg);
       ctx->graph_ev_used += 2;
       if (sg != st) {  // two lanes (never combined with L2 sub-chunking: gch == B there)
@@ -559,7 +563,7 @@ int tzr_ctx_destroy(tzr_ctx* ctx) {
   if (!ctx) return TZR_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->pk, &ctx->opnd, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
+  DevBuf* bufs[] = {&ctx->src, &ctx->dst, &ctx->sf, &ctx->df, &ctx->pk, &ctx->opnd, &ctx->tclist, &ctx->gc, &ctx->adj, &ctx->deg, &ctx->nedges,
                     &ctx->hclq, &ctx->hsize, &ctx->clq, &ctx->L, &ctx->alive, &ctx->best_bits, &ctx->alive_cnt, &ctx->root_ctr,
                     &ctx->lock, &ctx->flg, &ctx->kfinal, &ctx->tstart, &ctx->stack, &ctx->cv, &ctx->centry, &ctx->ps, &ctx->pd, &ctx->wgt,
                     &ctx->res, &ctx->skey, &ctx->sidx, &ctx->sorted, &ctx->rmask, &ctx->tmask, &ctx->sol, &ctx->dbg,
@@ -647,9 +651,8 @@ int tzr_graph_build(tzr_ctx* ctx, const double* src, const double* dst, int n, d
   CK(cudaMemcpyAsync((void*)bt.dst, dst, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
   if (ctx->flags & 6u) cudaMemsetAsync((void*)ctx->dbg.p, 0, 16 * sizeof(unsigned long long), st);
   launch_prep(bt, st);
-  launch_graph(bt, st, ctx->num_sms);
+  ctx->launches += 2 + launch_graph(bt, st, ctx->num_sms);
   launch_degree(bt, st);
-  ctx->launches += 3;
   rc = check_launch(ctx, "graph build");
   if (rc) return rc;
   CK(cudaMemcpy2DAsync(adj_bits, (size_t)words64(n) * 8, bt.adj, (size_t)pitch64(n) * 8, (size_t)words64(n) * 8, n,

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     // ---- tensor-core filter constants (graph_tc.cu; derivation in DESIGN.md §3.1).  a' = |ds|^2 and b' = |dd|^2 come
     // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb (E = ea + eb); the kernel forms t' = a'-b' and
     // d' = t'^2 - beta^2 (sqrt a' + sqrt b')^2 in FP32 and decides by the sign of d' unless
-    //   d'^2 <= t'^2 (k1 + k2 t'^2)   [ <= ( 7.5 E |t'| + 24 u t'^2 )^2 ... the band ]   or  a' < ga  or  b' < gb.
+    //   d'^2 <= t'^2 (k1 + k2 t'^2)   [ >= ( 16 E |t'| + 24 u t'^2 )^2 : the band ]   or  a' <= ga  or  b' <= gb.
     {
       double Ds2 = 0, Dd2 = 0;  // largest possible squared distance inside each (scaled) cloud
       for (int k = 0; k < 3; ++k) {
@@ -135,10 +135,13 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
       }
       const double kappa = bt.tc_kappa > 0 ? bt.tc_kappa : kTcKappa;
       const double ea = kappa * u32 * Ds2, eb = kappa * u32 * Dd2, E = ea + eb;
-      const double ct = 7.5 * E, cf = 24.0 * u32;
-      const double ga = (2.25 * beta * ea / E) * (2.25 * beta * ea / E), gb = (2.25 * beta * eb / E) * (2.25 * beta * eb / E);
+      // guards: sqrt(a') >= max(16 ea / beta, beta / 4) (same for b'): the first keeps |g' - g| <= beta/8, the second
+      // bounds the sqrt(b'/a') sensitivity of w near the threshold by 4.5; band constant 2.43 * (2 + 4.5) = 15.8
+      const double ra = fmax(16.0 * ea / beta, 0.25 * beta), rb = fmax(16.0 * eb / beta, 0.25 * beta);
+      const double ga = ra * ra, gb = rb * rb;
+      const double ct = 16.0 * E, cf = 24.0 * u32;
       const bool ok = !use64 && (bt.flags_dbg & 512u) == 0 && Ds2 > 0 && Dd2 > 0 && Ds2 < 1e8 && Dd2 < 1e8 &&
-                      E <= beta * beta / 8.0 && beta * beta > 1e-30 && isfinite(E);
+                      beta * beta > 1e-30 && isfinite(E) && ga <= Ds2 / 256.0 && gb <= Dd2 / 256.0;
       gc.use_tc = ok ? 1 : 0;
       gc.tc_beta2 = (float)(beta * beta);
       gc.tc_k1 = (float)(2.0 * ct * ct * up);
@@ -812,12 +815,13 @@ __global__ void __launch_bounds__(256) degree_kernel(Batch bt) {
 
 void launch_prep(const Batch& bt, cudaStream_t st) { prep_kernel<<<bt.B, 256, 0, st>>>(bt); }
 
-void launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
+int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
   Batch bt = bt0;
   // default: tensor-core kernel for every problem prep_kernel marked use_tc, CUDA-core strip kernel for the rest
   // (ill-conditioned filter, non-finite input); the A/B flags below run the CUDA-core kernels on everything
   bt.tc_active = (bt.flags_dbg & (8u | 16u | 32u | 64u | 128u | 256u | 512u)) ? 0 : 1;
-  if (bt.tc_active) launch_graph_tc(bt, st, num_sms);
+  int launches = 1;  // the CUDA-core strip kernel below (grid covers every problem; TC problems return at once)
+  if (bt.tc_active) launches += launch_graph_tc(bt, st, num_sms);
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)bt.B);
 #ifdef TZR_AB_KERNELS
@@ -826,7 +830,7 @@ void launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
       graph_tile_kernel<true><<<grid, kGraphThreads, 0, st>>>(bt);
     else
       graph_tile_kernel<false><<<grid, kGraphThreads, 0, st>>>(bt);
-    return;
+    return launches;
   }
 #endif
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
@@ -846,6 +850,7 @@ void launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
     graph_strip2_kernel<false, 8, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else  // packed FP32x2 strip kernel, 8 CTAs/SM, degrees fused
     graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  return launches;
 }
 
 bool graph_fuses_degrees(const Batch& bt) { return (bt.flags_dbg & (2u | 8u | 16u | 32u | 64u | 128u | 256u)) == 0; }

@@ -24,7 +24,7 @@
 // beta^2).  The sign bit of d is shifted straight into the row word (no compare, no ballot); whether any of the
 // thread's 32 pairs falls into the error band of the tensor-core norms (d^2 <= t^2 (k1 + k2 t^2), or a tiny a / b;
 // prep_kernel) is tracked with three 3-input FMNMX, and only then the warp revisits its chunk (re-read
-// from TMEM) and re-evaluates the flagged pairs with the reference's exact FP64 sequence.  7 issue slots + 1 MUFU per
+// from TMEM) and queues the flagged pairs; tc_patch_kernel re-evaluates them with the reference's exact FP64 sequence.  7 issue slots + 1 MUFU per
 // pair instead of ~20 + 2.
 // Output (packed symmetric bitset, fused degrees) is bit-identical to graph_build.cu's and to the oracle's.
 #include "tc_ptx.cuh"
@@ -46,7 +46,10 @@ constexpr int kTcBStages = 4;
 constexpr int kTcSmemBytes = 2 * kTcTileA + kTcBStages * kTcTileB + 256;
 
 __host__ __device__ inline size_t tc_a_bytes(int n) { return (size_t)((n + 127) / 128) * kTcTileA; }
-__host__ __device__ inline size_t tc_b_bytes(int n) { return (size_t)((n + kTcN - 1) / kTcN) * kTcTileB; }
+// 64-column blocks per problem: the whole padded row pitch (2 per 128-block), so that every word of the bitset rows is
+// written (all-zero operands past n give masked, i.e. zero, words)
+__host__ __device__ inline int tc_nt64(int n) { return 2 * ((n + 127) / 128); }
+__host__ __device__ inline size_t tc_b_bytes(int n) { return (size_t)tc_nt64(n) * kTcTileB; }
 size_t tc_operand_bytes(int B, int n) { return (size_t)B * (tc_a_bytes(n) + tc_b_bytes(n)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -74,7 +77,6 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
   float4* outA = reinterpret_cast<float4*>(base + (size_t)blk * kTcTileA);
   float4* outB = reinterpret_cast<float4*>(base + tc_a_bytes(n) + (size_t)(2 * blk + (r >> 6)) * kTcTileB);
   const int rb = r & 63;
-  const bool haveB = 2 * blk + (r >> 6) < (n + kTcN - 1) / kTcN;  // the last 128-block may own only one 64-block
   const double* src = bt.src + (size_t)b * n * 3;
   const double* dst = bt.dst + (size_t)b * n * 3;
 #pragma unroll
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
     A[3 * 128 + r] = make_float4(c[0][1], c[1][1], c[2][1], one);
     A[4 * 128 + r] = make_float4(c[0][0], c[1][0], c[2][0], one);
     A[5 * 128 + r] = make_float4(c[0][2], c[1][2], c[2][2], one);
-    if (haveB) {
+    {
       Bq[0 * kTcN + rb] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], one);
       Bq[1 * kTcN + rb] = make_float4(-2.f * c[0][1], -2.f * c[1][1], -2.f * c[2][1], one);
       Bq[2 * kTcN + rb] = make_float4(-2.f * c[0][0], -2.f * c[1][0], -2.f * c[2][0], one);
@@ -128,7 +130,7 @@ struct TileIter {
     spp = spp_;
     S = S_;
     nt = (n + kTile - 1) / kTile;
-    nt64 = (n + kTcN - 1) / kTcN;
+    nt64 = tc_nt64(n);
     b = I = 0;
     J = J1 = 0;
     first = false;
@@ -159,7 +161,7 @@ struct TileIter {
 };
 
 __host__ __device__ inline int tc_strips_per_problem(int n, int S) {
-  const int nt = (n + kTile - 1) / kTile, nt64 = (n + kTcN - 1) / kTcN;
+  const int nt = (n + kTile - 1) / kTile, nt64 = tc_nt64(n);
   int total = 0;
   for (int I = 0; I < nt; ++I) total += (nt64 - 2 * I + S - 1) / S;
   return total;
@@ -227,22 +229,37 @@ __device__ __forceinline__ void tc_pair2(uint32_t a0, uint32_t a1, uint32_t b0, 
 }
 
 // 16 pairs (columns c0 .. c0+15 of the warp's 32): shifts their sign bits into `word` (call with the upper half first)
-// and folds the band / guard minima
+// and folds the band / guard minima.  Two phases so that the eight MUFU pairs are in flight together: with the
+// consumer right behind each MUFU.SQRT a warp stalls for the XU latency once per pair group (measured: ~50 clk per
+// pair step per warp, latency-bound at 16 warps per SM).
 __device__ __forceinline__ void tc_sweep16(uint32_t ta, uint32_t tb, const TcConsts& k, uint32_t& word, float& m1,
                                            float& ma, float& mb) {
   uint32_t ra[16], rb[16];
   tmem_ld16(ta, ra);
   tmem_ld16(tb, rb);
   tmem_wait_ld();
+  f32x2 T[8], Sm[8], Q[8];
 #pragma unroll
-  for (int c = 14; c >= 0; c -= 2) {
+  for (int g = 0; g < 8; ++g) {
+    const f32x2 A = pk2(ra[2 * g], ra[2 * g + 1]), B = pk2(rb[2 * g], rb[2 * g + 1]);
+    T[g] = sub2(A, B);
+    Sm[g] = add2(A, B);
+    float p0, p1;
+    upk2(mul2(A, B), p0, p1);
+    Q[g] = pk2f(sqrt_approx_tc(p0), sqrt_approx_tc(p1));
+    ma = fminf(ma, fminf(__uint_as_float(ra[2 * g]), __uint_as_float(ra[2 * g + 1])));
+    mb = fminf(mb, fminf(__uint_as_float(rb[2 * g]), __uint_as_float(rb[2 * g + 1])));
+  }
+#pragma unroll
+  for (int g = 7; g >= 0; --g) {
+    const f32x2 w = fma2(Q[g], k.two, Sm[g]), t2 = mul2(T[g], T[g]), d = fma2(w, k.nbeta2, t2);
+    const f32x2 nz = fma2(t2, k.nk2, k.nk1), ny = mul2(t2, nz), r = fma2(d, d, ny);
     float d0, d1, r0, r1;
-    tc_pair2(ra[c], ra[c + 1], rb[c], rb[c + 1], k, d0, d1, r0, r1);
+    upk2(d, d0, d1);
+    upk2(r, r0, r1);
     word = __funnelshift_l(__float_as_uint(d1), word, 1);
     word = __funnelshift_l(__float_as_uint(d0), word, 1);
     m1 = fminf(m1, fminf(r0, r1));
-    ma = fminf(ma, fminf(__uint_as_float(ra[c]), __uint_as_float(ra[c + 1])));
-    mb = fminf(mb, fminf(__uint_as_float(rb[c]), __uint_as_float(rb[c + 1])));
   }
 }
 
@@ -320,9 +337,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
       ld.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
       mm.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
       uint32_t n_loaded = 0, n_strips_loaded = 0, n_mma = 0, n_strips = 0, ap = 0;
+      int tc_b = -1;
+      bool tc_ok = false;
       auto next_tc = [&](TileIter& t) {  // next tile of a problem that takes the tensor-core path
-        while (t.next())
-          if (bt.gc[t.b].use_tc) return true;
+        while (t.next()) {
+          if (t.b != tc_b) {
+            tc_b = t.b;
+            tc_ok = bt.gc[t.b].use_tc != 0;
+          }
+          if (tc_ok) return true;
+        }
         return false;
       };
       auto issue_load = [&](const TileIter& t) {
@@ -398,9 +422,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
     kc.two = pk2f(2.f, 2.f);
     kc.nbeta2 = kc.nk1 = kc.nk2 = kc.two;
     kc.ga = kc.gb = 0.f;
+    const GraphConsts* gcp = bt.gc;
+    bool use_tc = false;
     while (ti.next()) {
-      const GraphConsts* gcp = bt.gc + ti.b;
-      if (!gcp->use_tc) continue;
+      if (ti.first) {  // per strip, not per tile: the load sits on the critical path of the tile hand-off
+        gcp = bt.gc + ti.b;
+        use_tc = gcp->use_tc != 0;
+      }
+      if (!use_tc) continue;
       const int b = ti.b, I = ti.I, J = ti.J;
       if (ti.first) {
         kc.nbeta2 = pk2f(-gcp->tc_beta2, -gcp->tc_beta2);
@@ -428,7 +457,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
       if (i >= j0 && i < j0 + 32) vmask &= ~(1u << (i - j0));
       const bool flagged = !(m1 > 0.f) || !(ma > kc.ga) || !(mb > kc.gb);
       if (kVerify || __any_sync(0xffffffffu, flagged && vmask != 0u)) {
-        // ---- rare: find the undecided pairs of this thread and re-evaluate them with the exact FP64 sequence
+        // ---- rare: find the undecided pairs of this thread.  They keep their tentative bit (sign of d) and are queued
+        // for tc_patch_kernel, which evaluates the reference's exact FP64 sequence and flips the bits that disagree —
+        // so no warp of this kernel waits for double-precision square roots while seven others wait for its
+        // accumulator stage.  (Queue full: evaluated here.)
         uint32_t fmask = tc_flags16(ta, tb, kc) | (tc_flags16(ta + 16u, tb + 16u, kc) << 16);
         fmask &= vmask;
         const double* src = bt.src + (size_t)b * n * 3;
@@ -447,17 +479,39 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
           }
           if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
         }
-        int nre = 0;
-        while (fmask) {
-          const int k = __ffs(fmask) - 1;
-          fmask &= fmask - 1;
-          const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j0 + k, beta, s_hat) : edge_exact(src, dst, i, j0 + k, beta);
-          word = (word & ~(1u << k)) | ((ex ? 1u : 0u) << k);
-          ++nre;
+        const int cnt = __popc(fmask);
+        int incl = cnt;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
         }
-        if (bt.rechecks) {
-          nre = __reduce_add_sync(0xffffffffu, nre);
-          if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+          unsigned int base = 0;
+          if (lane == 0) base = atomicAdd(bt.tc_list_count, (unsigned int)total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (base + (unsigned int)total <= bt.tc_list_cap) {
+            unsigned int pos = base + (unsigned int)(incl - cnt);
+            while (fmask) {
+              const int k = __ffs(fmask) - 1;
+              fmask &= fmask - 1;
+              bt.tc_list[pos++] = make_uint2((unsigned int)b, ((unsigned int)i << 16) | (unsigned int)(j0 + k));
+            }
+          } else {  // queue full (the count keeps growing; the patch kernel clamps it): exact evaluation in place
+            int nre = 0;
+            while (fmask) {
+              const int k = __ffs(fmask) - 1;
+              fmask &= fmask - 1;
+              const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j0 + k, beta, s_hat) : edge_exact(src, dst, i, j0 + k, beta);
+              word = (word & ~(1u << k)) | ((ex ? 1u : 0u) << k);
+              ++nre;
+            }
+            if (bt.rechecks) {
+              nre = __reduce_add_sync(0xffffffffu, nre);
+              if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
+            }
+          }
         }
       }
       // hand the accumulator stage back to the MMA issuer (all TMEM reads of this warp are complete)
@@ -487,6 +541,38 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
   if (warp == kTcEpiWarps) tmem_dealloc<256>(tbase);
 }
 
+// ------------------------------------------------------------------------------------------------
+// exact re-check of the queued pairs: one thread per entry.  The bit written by graph_tc_kernel is the tentative
+// classification; if the reference's FP64 sequence disagrees the bit (and its mirror, unless both directions live in the
+// same diagonal 128-block and were queued separately) is flipped and the degrees are adjusted.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_patch_kernel(Batch bt) {
+  const unsigned int count = min(*bt.tc_list_count, bt.tc_list_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bt.rechecks) atomicAdd(bt.rechecks, (unsigned long long)count);
+  const int n = bt.n, P32 = pitch32(n);
+  const bool scale_mode = bt.scale_mode != 0;
+  for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const uint2 ent = bt.tc_list[e];
+    const int b = (int)ent.x, i = (int)(ent.y >> 16), j = (int)(ent.y & 0xffffu);
+    const double* src = bt.src + (size_t)b * n * 3;
+    const double* dst = bt.dst + (size_t)b * n * 3;
+    const double beta = bt.gc[b].beta;
+    const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, bt.sol[b].scale) : edge_exact(src, dst, i, j, beta);
+    uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * P32;
+    const bool cur = (adj32[(size_t)i * P32 + (j >> 5)] >> (j & 31)) & 1u;
+    if (ex != cur) {
+      int* degp = bt.deg + (size_t)b * n;
+      const int dd = ex ? 1 : -1;
+      atomicXor(adj32 + (size_t)i * P32 + (j >> 5), 1u << (j & 31));
+      atomicAdd(degp + i, dd);
+      if ((i >> 7) != (j >> 7)) {  // off-diagonal block: the transposed bit came from the same evaluation
+        atomicXor(adj32 + (size_t)j * P32 + (i >> 5), 1u << (i & 31));
+        atomicAdd(degp + j, dd);
+      }
+    }
+  }
+}
+
 int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   static bool attr_done_dev[64] = {};
   int dev = 0;
@@ -498,6 +584,7 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   }
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 pg((unsigned)nt, (unsigned)bt.B);
+  cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);
   tc_prep_kernel<<<pg, 128, 0, st>>>(bt);
   // strip length (in 64-column tiles): long strips amortise the A tile, short ones balance small batches
   const int ctas = 2 * num_sms;
@@ -510,7 +597,17 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
     graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
   else
     graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
-  return 2;
+  tc_patch_kernel<<<4 * num_sms, 256, 0, st>>>(bt);
+  return 3;
+}
+
+// entries of the re-check queue for a (B, n) batch: 1/256 of the pairs (the band is ~1e-4), at least 1 Mi, at most 64 Mi
+size_t tc_list_entries(int B, int n) {
+  const double pairs = 0.5 * (double)B * (double)n * (double)n;
+  double c = pairs / 256.0;
+  if (c < 1048576.0) c = 1048576.0;
+  if (c > 67108864.0) c = 67108864.0;
+  return (size_t)c;
 }
 
 }  // namespace tzr

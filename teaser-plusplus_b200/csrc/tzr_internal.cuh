@@ -61,6 +61,9 @@ struct Batch {
   float4* df;
   float* opnd;    // B * ceil(n/128) * 2 roles * 2 clouds * 6 planes * 128 rows * 4: tf32-split MMA operand tiles of the
                   // tensor-core graph kernel (graph_tc.cu), written by tc_prep_kernel
+  uint2* tc_list;         // re-check queue of the tensor-core graph kernel: (problem, i << 16 | j)
+  unsigned int* tc_list_count;  // 1 (may exceed the capacity: writers past it evaluate in place)
+  unsigned int tc_list_cap;
   float* pk;      // B*6*npad128(n): the same centred floats, pair-interleaved per 128-column block for the packed
                   // FP32x2 graph kernel (arrays sx,sy,sz,dx,dy,dz; element of point j at blk*128 + k*64 + lane*2 + half)
   GraphConsts* gc;        // B
@@ -139,10 +142,11 @@ static __device__ __noinline__ bool edge_exact_scale(const double* __restrict__ 
 
 // kernels (defined in the .cu files) -------------------------------------------------------------
 void launch_prep(const Batch& bt, cudaStream_t st);
-void launch_graph(const Batch& bt, cudaStream_t st, int num_sms);
+int launch_graph(const Batch& bt, cudaStream_t st, int num_sms);  // returns the number of kernels launched
 // graph_tc.cu: tensor-core path (operand tiles + tcgen05 kernel) for the problems prep_kernel marked use_tc
 int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms);
 size_t tc_operand_bytes(int B, int n);
+size_t tc_list_entries(int B, int n);
 // bitset_only: the adjacency did not come from launch_graph (tzr_max_clique on a caller's bitset): always popcount
 void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only = false);
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);
