@@ -271,7 +271,8 @@ def main():
     clq_d = torch.zeros((B, n), dtype=torch.int32, device="cuda")
     params = solver_params(capi, cfg, nb, args.estimate_scaling)
     ctx = capi.Context(local_rank)
-    base_flags = int(os.environ.get("TZR_FLAGS", "0"))  # debug / A-B switches of the library (512 = CUDA-core graph kernel)
+    base_flags = int(os.environ.get("TZR_FLAGS", "0"))  # debug / A-B switches of the library (1024 = tensor-core graph
+    # kernel, 2048 = round-1 graph kernel)
     ctx.set_flags(base_flags)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -400,7 +401,8 @@ def main():
                 traffic = prof.get("dram_bytes_per_problem") * B
         except Exception:
             pass
-        tc = not (base_flags & 512)
+        kern = ("graph_tc_kernel (+ tc_prep_kernel, tc_patch_kernel)" if base_flags & 1024 else
+                "graph_strip2_kernel (round-1 kernel)" if base_flags & 2048 else "graph_strip3_kernel (+ tc_patch_kernel)")
         line = {
             "metric": "registrations/sec", "value": value, "unit": "registrations/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": t_dev_max / K, "higher_is_better": True, "scaling": C["scaling"],
@@ -414,8 +416,8 @@ def main():
                        if flush is None else
                        f"working set {step_bytes / 1e6:.0f} MB per step: 256 MB L2 flush between steps (its {t_flush / K:.3f} ms "
                        f"per step is subtracted from ms_per_step)"),
-                "dtype_note": "FP64 predicate/GNC/TLS; the graph stage classifies pairs from tensor-core (tf32x3 split) "
-                              "squared norms in FP32 and re-checks the undecided band in exact FP64 (bit-identical bitset)",
+                "dtype_note": "FP64 predicate/GNC/TLS; the graph stage classifies pairs with an FP32 interval test on centred "
+                              "float copies and re-checks the undecided band in exact FP64 (bit-identical bitset)",
             },
             "e2e": {"value": e2e, "unit": "registrations/s", "h2d_bytes_per_step": int(2 * B * n * 24),
                     # what tzr_solve_batch copies back: the solution records + the used prefix of every clique row
@@ -428,14 +430,13 @@ def main():
                         "stage_ms_last_call": lat_stage},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "graph_tc_kernel (+ tc_prep_kernel)" if tc else "graph_strip2_kernel",
+            "roofline": {"bound": "hbm", "kernel": kern,
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": bytes_graph(n) * B, "kernel_ms": g_ms,
                          "note": "graph stage = O(N^2) pair classification; SURVEY §8d defines its roofline against HBM "
                                  "(algorithmic bytes: points in, packed bitset + degrees out).  The binding resource is "
-                                 "the per-pair arithmetic (1 MUFU + 6 issue slots per pair after moving the squared norms "
-                                 "to the tensor cores), not DRAM"},
+                                 "the per-pair arithmetic (12.5 issue slots + 1 MUFU per 32 pairs), not DRAM"},
             "stage_ms_per_step": {k_: v / max(n_calls, 1) for k_, v in stage_sum.items()},
             "counters": {"graph_exact_rechecks_per_problem": counters["filter_rechecks"] / B,
                          "clique_search_nodes_per_problem": counters["clique_nodes"] / B},

@@ -265,7 +265,8 @@ int tzr_solve_batch_multi(const int32_t* devices, int n_devices, const tzr_param
 /* Debug/verification switches: bit 0 (1) = force the pure-FP64 graph predicate (no FP32 filter),
  * bit 1 (2) = verify the FP32 / tensor-core filter against FP64 for every pair and count mismatches,
  * bit 2 (4) = count exact re-checks and clique search nodes, bit 8 (256) = degrees by a separate pass,
- * bit 9 (512) = CUDA-core graph kernel for every problem (no tensor-core path). */
+ * bit 10 (1024) = build the graph with the tensor-core kernel (tcgen05 Gram norms; bit-identical, measured slower than
+ * the default CUDA-core kernel on B200: DESIGN.md 3.1), bit 9 (512) overrides it. */
 int tzr_ctx_set_flags(tzr_ctx* ctx, uint32_t flags);
 int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx);
 /* Number of pairs of the most recent graph build that needed the exact FP64 re-check. */

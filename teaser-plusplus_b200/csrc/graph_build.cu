@@ -122,6 +122,26 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
     gc.b2 = use64 ? __int_as_float(0x7f800000) : (float)(gam2 * up);
     gc.use_fp64 = use64;
     gc.s_hat = s_hat;
+    // ---- v7 strip kernel (graph_strip3_kernel): d_hi = t^2 - (beta^2 - K) w < 0 proves an edge, d_lo = t^2 -
+    // (beta^2 + K) w >= 0 proves a non-edge, K = dt (2 beta + dt) + 32 u beta^2 relative to w = (sqrt a + sqrt b)^2.
+    // dt bounds |g' - g|: float conversion of the centred coordinates (<= u M each), the differences, squares and sums
+    // give |sqrt a' - sqrt a| <= ~15 u M per cloud; 64 u (Ms + Md) is used, plus the bias eps of the squared norms.
+    {
+      const double d3 = 64.0 * u32 * (Ms + Md);
+      const double eps = fmax((d3 / 16.0) * (d3 / 16.0), 1e-36);
+      const double dt = 1.125 * d3;
+      const double K = dt * (2.0 * beta + dt) + 32.0 * u32 * beta * beta;
+      const double b2v = beta * beta;
+      gc.f3_eps = (float)eps;
+      if (use64) {  // exact path for every pair (the kernel also overrides the words: NaN inputs have no sign)
+        gc.f3_nlo = -__int_as_float(0x7f800000);
+        gc.f3_nhi = __int_as_float(0x7f800000);
+      } else {
+        gc.f3_nlo = (float)(-(b2v + K) * up);
+        gc.f3_nhi = (b2v - K > 0) ? (float)(-(b2v - K) * dn) : (float)((K - b2v) * up + 1e-37);
+      }
+      gc.pad2 = 0;
+    }
     // ---- tensor-core filter constants (graph_tc.cu; derivation in DESIGN.md §3.1).  a' = |ds|^2 and b' = |dd|^2 come
     // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb (E = ea + eb); the kernel forms t' = a'-b' and
     // d' = t'^2 - beta^2 (sqrt a' + sqrt b')^2 in FP32 and decides by the sign of d' unless
@@ -140,7 +160,7 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
       const double ra = fmax(16.0 * ea / beta, 0.25 * beta), rb = fmax(16.0 * eb / beta, 0.25 * beta);
       const double ga = ra * ra, gb = rb * rb;
       const double ct = 16.0 * E, cf = 24.0 * u32;
-      const bool ok = !use64 && (bt.flags_dbg & 512u) == 0 && Ds2 > 0 && Dd2 > 0 && Ds2 < 1e8 && Dd2 < 1e8 &&
+      const bool ok = !use64 && (bt.flags_dbg & 1024u) != 0 && (bt.flags_dbg & 512u) == 0 && Ds2 > 0 && Dd2 > 0 && Ds2 < 1e8 && Dd2 < 1e8 &&
                       beta * beta > 1e-30 && isfinite(E) && ga <= Ds2 / 256.0 && gb <= Dd2 / 256.0;
       gc.use_tc = ok ? 1 : 0;
       gc.tc_beta2 = (float)(beta * beta);
@@ -771,6 +791,205 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel
   if (kFuseDeg && lane < nrows && rdeg) atomicAdd(degp + ibase + lane, rdeg);
 }
 
+// ------------------------------------------------------------------------------------------------
+// graph strip kernel v7 (default): same decomposition, inputs and outputs as graph_strip2_kernel, cheaper pair test.
+//   * one MUFU per pair instead of two: with t = a-b, s = a+b, q = sqrt(ab), w = s + 2q = (sqrt a + sqrt b)^2 the pair
+//     is an edge iff d = t^2 - beta^2 w <= 0 (d = w (g^2 - beta^2), g = |sqrt a - sqrt b|); both sides of the
+//     comparison are equal at the threshold, so the FP32 evaluation error is a few ulp of beta^2 w;
+//   * no compares and no ballots: d_hi = t^2 - (beta^2 - K) w and d_lo = t^2 - (beta^2 + K) w are formed with two
+//     packed FFMA, their SIGN BITS are funnel-shifted into two per-lane column words (sure edge / edge-or-undecided);
+//     K = delta (2 beta + delta) + 32 u beta^2 with delta >= |g' - g| (FP32 error of the centred float pipeline), so
+//     sign(d_hi) = 1 proves g < beta and sign(d_lo) = 0 proves g > beta;
+//   * undecided pairs = lo & ~hi (~3e-6 of the pairs on C2) keep the tentative bit 0 and are queued for
+//     tc_patch_kernel (exact FP64 sequence, flips the bit if needed); queue full -> evaluated in place;
+//   * the lane's column words ARE the transposed half of the bitset; the row words come from the same 5-stage
+//     warp-shuffle transpose as before.
+// Per 32 pairs: 12.5 issue slots + 1 MUFU instead of 20 + 2.  a, b >= eps > 0 (eps is folded into the first FMA of each
+// squared norm) so w > 0 and zero-length TIM pairs (duplicate correspondences) are classified like any other pair.
+// ------------------------------------------------------------------------------------------------
+template <bool kVerify, int kMinBlocks>
+__global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip3_kernel(Batch bt) {
+  const int b = blockIdx.y;
+  const int n = bt.n;
+  const int nt = (n + kTile - 1) / kTile;
+  int I = 0, p = blockIdx.x;
+  while (true) {
+    const int ng = (nt - I + kStripBlocks - 1) / kStripBlocks;
+    if (p < ng) break;
+    p -= ng;
+    ++I;
+  }
+  const int J0 = I + p * kStripBlocks;
+  const int J1 = min(nt, J0 + kStripBlocks);
+
+  __shared__ IPointNeg2 s_ip[kTile];
+
+  const GraphConsts* gcp = bt.gc + b;
+  if (bt.tc_active && gcp->use_tc) return;  // built by graph_tc_kernel
+  const f32x2 nlo = pk2(gcp->f3_nlo, gcp->f3_nlo), nhi = pk2(gcp->f3_nhi, gcp->f3_nhi), two = pk2(2.f, 2.f);
+  const f32x2 eps2 = pk2(gcp->f3_eps, gcp->f3_eps);
+  const double beta = gcp->beta;
+  const bool scale_mode = bt.scale_mode != 0;
+  const double s_hat = scale_mode ? bt.sol[b].scale : 1.0;
+
+  const float4* sf = bt.sf + (size_t)b * n;
+  const float4* df = bt.df + (size_t)b * n;
+  const double* src = bt.src + (size_t)b * n * 3;
+  const double* dst = bt.dst + (size_t)b * n * 3;
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int ibase = I * kTile + 32 * w;
+  const int nrows = min(32, n - ibase);
+  if (nrows <= 0) return;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int i = ibase + lane;
+    const float4 s = (i < n) ? sf[i] : z4, d = (i < n) ? df[i] : z4;
+    IPointNeg2 ip;
+    ip.a = make_float4(-s.x, -s.x, -s.y, -s.y);
+    ip.b = make_float4(-s.z, -s.z, -d.x, -d.x);
+    ip.c = make_float4(-d.y, -d.y, -d.z, -d.z);
+    s_ip[tid] = ip;
+  }
+  __syncwarp();
+  uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * pitch32(n);
+  const int P32 = pitch32(n);
+  const uint32_t rmask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
+
+  const int npadh = npad128(n) / 2;  // 64-bit elements per packed array
+  const f32x2* pkp = reinterpret_cast<const f32x2*>(bt.pk + (size_t)b * 6 * npad128(n));
+  int* degp = bt.deg + (size_t)b * n;
+  int rdeg = 0;
+  for (int J = J0; J < J1; ++J) {
+    const int jb = J * kTile + lane;
+    f32x2 SX[2], SY[2], SZ[2], DX[2], DY[2], DZ[2];
+    bool vj[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      vj[2 * k] = jb + 64 * k < n;
+      vj[2 * k + 1] = jb + 64 * k + 32 < n;
+      const size_t e = (size_t)J * 64 + k * 32 + lane;
+      SX[k] = pkp[0 * (size_t)npadh + e]; SY[k] = pkp[1 * (size_t)npadh + e]; SZ[k] = pkp[2 * (size_t)npadh + e];
+      DX[k] = pkp[3 * (size_t)npadh + e]; DY[k] = pkp[4 * (size_t)npadh + e]; DZ[k] = pkp[5 * (size_t)npadh + e];
+    }
+    // column words of this lane: bit ii = pair (row ibase+ii, column jb + 32c); hi = surely an edge, lo = edge or undecided
+    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+    // rows are visited from the last to the first so that the funnel shift leaves row ii at bit ii
+#pragma unroll 2
+    for (int ii = 31; ii >= 0; --ii) {
+      const ulonglong2* ipp = reinterpret_cast<const ulonglong2*>(&s_ip[32 * w + ii]);
+      const ulonglong2 qa = ipp[0], qb = ipp[1], qc = ipp[2];
+      const f32x2 nsx = qa.x, nsy = qa.y, nsz = qb.x, ndx = qb.y, ndy = qc.x, ndz = qc.y;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const f32x2 ax = add2(SX[k], nsx), ay = add2(SY[k], nsy), az = add2(SZ[k], nsz);
+        const f32x2 bx = add2(DX[k], ndx), by = add2(DY[k], ndy), bz = add2(DZ[k], ndz);
+        const f32x2 a = fma2(az, az, fma2(ay, ay, fma2(ax, ax, eps2)));
+        const f32x2 bb = fma2(bz, bz, fma2(by, by, fma2(bx, bx, eps2)));
+        const f32x2 t = sub2(a, bb), s = add2(a, bb);
+        float p0, p1;
+        upk2(mul2(a, bb), p0, p1);
+        const f32x2 q = pk2(sqrt_approx(p0), sqrt_approx(p1));
+        const f32x2 ww = fma2(q, two, s), t2 = mul2(t, t);
+        float h0, h1, l0, l1;
+        upk2(fma2(ww, nhi, t2), h0, h1);
+        upk2(fma2(ww, nlo, t2), l0, l1);
+        hi[2 * k] = __funnelshift_l(__float_as_uint(h0), hi[2 * k], 1);
+        hi[2 * k + 1] = __funnelshift_l(__float_as_uint(h1), hi[2 * k + 1], 1);
+        lo[2 * k] = __funnelshift_l(__float_as_uint(l0), lo[2 * k], 1);
+        lo[2 * k + 1] = __funnelshift_l(__float_as_uint(l1), lo[2 * k + 1], 1);
+      }
+    }
+    // ---- validity (rows < n, columns < n, i != j), undecided pairs, tentative column words
+    uint32_t colw[4];
+    int nflag = 0;
+    if (gcp->use_fp64) {  // exact path for every pair (non-finite input, huge range, debug flag 1)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        hi[c] = 0u;
+        lo[c] = 0xffffffffu;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t vm = vj[c] ? rmask : 0u;
+      if (I == J && c == w) vm &= ~(1u << lane);  // column 32c + lane of the diagonal block meets row 32w + lane
+      uint32_t fm = lo[c] & ~hi[c] & vm;
+      colw[c] = hi[c] & vm;
+      if (kVerify) {  // every DECIDED pair is re-evaluated exactly; disagreements are counted (must stay 0)
+        uint32_t dm = vm & ~fm;
+        int bad = 0;
+        while (dm) {
+          const int ii = __ffs(dm) - 1;
+          dm &= dm - 1;
+          const int i = ibase + ii, j = jb + 32 * c;
+          const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
+          bad += (ex != (((colw[c] >> ii) & 1u) != 0u));
+        }
+        if (bad) atomicAdd(bt.mismatches, (unsigned long long)bad);
+      }
+      lo[c] = fm;  // re-used: undecided mask of column c
+      nflag += __popc(fm);
+    }
+    if (__any_sync(0xffffffffu, nflag != 0)) {
+      // ---- rare: queue the undecided pairs for tc_patch_kernel (their tentative bit is 0); queue full: exact here
+      int incl = nflag;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(bt.tc_list_count, (unsigned int)total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const bool queued = base + (unsigned int)total <= bt.tc_list_cap;
+      unsigned int pos = base + (unsigned int)(incl - nflag);
+      int nre = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t fm = lo[c];
+        const int j = jb + 32 * c;
+        while (fm) {
+          const int ii = __ffs(fm) - 1;
+          fm &= fm - 1;
+          const int i = ibase + ii;
+          if (queued) {
+            // the patch kernel flips bit (i, j) and, off the diagonal block, its mirror; the diagonal block holds both
+            // orientations as separate pairs, each queued by the lane that owns its column
+            bt.tc_list[pos++] = make_uint2((unsigned int)b, ((unsigned int)i << 16) | (unsigned int)j);
+          } else {
+            const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j, beta, s_hat) : edge_exact(src, dst, i, j, beta);
+            colw[c] |= (ex ? 1u : 0u) << ii;
+            ++nre;
+          }
+        }
+      }
+      if (bt.rechecks && !queued) {
+        nre = __reduce_add_sync(0xffffffffu, nre);
+        if (lane == 0 && nre) atomicAdd(bt.rechecks, (unsigned long long)nre);
+      }
+    }
+    // ---- row words (lane = row ibase + lane) by transposition; stores; fused degrees
+    uint32_t roww[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) roww[c] = warp_transpose32(colw[c], lane);
+    if (lane < nrows)
+      *reinterpret_cast<uint4*>(adj32 + (size_t)(ibase + lane) * P32 + 4 * J) =
+          make_uint4(roww[0], roww[1], roww[2], roww[3]);
+    rdeg += __popc(roww[0]) + __popc(roww[1]) + __popc(roww[2]) + __popc(roww[3]);
+    if (I != J) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (vj[c]) {
+          adj32[(size_t)(jb + 32 * c) * P32 + 4 * I + w] = colw[c];
+          if (colw[c]) atomicAdd(degp + jb + 32 * c, __popc(colw[c]));
+        }
+    }
+  }
+  if (lane < nrows && rdeg) atomicAdd(degp + ibase + lane, rdeg);
+}
+
 // n_edges2[b] = sum of degrees (the fused-degree path has no degree kernel to do it)
 __global__ void __launch_bounds__(256) edge_count_kernel(Batch bt) {
   const int b = blockIdx.x, n = bt.n;
@@ -817,9 +1036,9 @@ void launch_prep(const Batch& bt, cudaStream_t st) { prep_kernel<<<bt.B, 256, 0,
 
 int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
   Batch bt = bt0;
-  // default: tensor-core kernel for every problem prep_kernel marked use_tc, CUDA-core strip kernel for the rest
-  // (ill-conditioned filter, non-finite input); the A/B flags below run the CUDA-core kernels on everything
-  bt.tc_active = (bt.flags_dbg & (8u | 16u | 32u | 64u | 128u | 256u | 512u)) ? 0 : 1;
+  // default: CUDA-core strip kernel.  Debug flag 1024 routes every problem prep_kernel marked use_tc through the
+  // tensor-core kernel instead (bit-identical output, measured slower: DESIGN.md §3.1, profiles/r02_graph_tc_*)
+  bt.tc_active = ((bt.flags_dbg & 1024u) && !(bt.flags_dbg & (8u | 16u | 32u | 64u | 128u | 256u | 512u))) ? 1 : 0;
   int launches = 1;  // the CUDA-core strip kernel below (grid covers every problem; TC problems return at once)
   if (bt.tc_active) launches += launch_graph_tc(bt, st, num_sms);
   const int nt = (bt.n + kTile - 1) / kTile;
@@ -834,8 +1053,14 @@ int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
   }
 #endif
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
-  if (bt.flags_dbg & 2u)
-    graph_strip2_kernel<true, 5, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  if (!bt.tc_active) cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);  // (launch_graph_tc zeroes it otherwise)
+  bool v7 = false;
+  if (bt.flags_dbg & 2048u) {  // round-1 kernel (two MUFU, compares + ballots), A/B against the v7 default
+    if (bt.flags_dbg & 2u)
+      graph_strip2_kernel<true, 5, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    else
+      graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  }
 #ifdef TZR_AB_KERNELS
   else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
     graph_strip_kernel<false, 6><<<sgrid, kGraphThreads, 0, st>>>(bt);
@@ -848,12 +1073,26 @@ int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
 #endif
   else if (bt.flags_dbg & 256u)  // degrees by the separate degree kernel (A/B against the fused default)
     graph_strip2_kernel<false, 8, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else  // packed FP32x2 strip kernel, 8 CTAs/SM, degrees fused
-    graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  else {
+    v7 = true;
+    if (bt.flags_dbg & 2u)
+      graph_strip3_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
+    else
+      graph_strip3_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
+  }
+  if (v7) {  // exact re-check of the pairs the strip kernel queued
+    launch_graph_patch(bt, st, num_sms);
+    ++launches;
+  }
   return launches;
 }
 
-bool graph_fuses_degrees(const Batch& bt) { return (bt.flags_dbg & (2u | 8u | 16u | 32u | 64u | 128u | 256u)) == 0; }
+// fused degrees: the v7 default (also in verify mode) and the plain round-1 kernel
+bool graph_fuses_degrees(const Batch& bt) {
+  if (bt.flags_dbg & (8u | 16u | 32u | 64u | 128u | 256u)) return false;
+  if (bt.flags_dbg & 2048u) return (bt.flags_dbg & 2u) == 0;
+  return true;
+}
 
 void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only) {
   if (!bitset_only && graph_fuses_degrees(bt)) {  // degrees were accumulated by the graph kernel; only the edge count is left

@@ -598,8 +598,11 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   else
     graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
   tc_patch_kernel<<<4 * num_sms, 256, 0, st>>>(bt);
+  cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);  // the strip kernel (other problems) queues next
   return 3;
 }
+
+void launch_graph_patch(const Batch& bt, cudaStream_t st, int num_sms) { tc_patch_kernel<<<4 * num_sms, 256, 0, st>>>(bt); }
 
 // entries of the re-check queue for a (B, n) batch: 1/256 of the pairs (the band is ~1e-4), at least 1 Mi, at most 64 Mi
 size_t tc_list_entries(int B, int n) {

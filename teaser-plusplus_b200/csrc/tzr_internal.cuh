@@ -38,6 +38,9 @@ struct GraphConsts {
   int pad;
   double beta;    // 2*noise_bound*sqrt(cbar2)
   double cs[3], cd[3];  // centres subtracted before the float conversion
+  float f3_nlo, f3_nhi;  // graph_strip3_kernel: -(beta^2 + K), -(beta^2 - K)   (K: undecided band relative to w)
+  float f3_eps;          // bias of the squared norms (keeps w > 0)
+  int pad2;
   double s_hat;   // scale applied to the centred source copies (1 unless estimate_scaling)
   // tensor-core filter (graph_tc.cu): d = (a-b)^2 - beta^2 (sqrt(a)+sqrt(b))^2 from the Gram-form squared norms
   int use_tc;     // 1: this problem goes through graph_tc_kernel, 0: through the CUDA-core strip kernel
@@ -147,6 +150,7 @@ int launch_graph(const Batch& bt, cudaStream_t st, int num_sms);  // returns the
 int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms);
 size_t tc_operand_bytes(int B, int n);
 size_t tc_list_entries(int B, int n);
+void launch_graph_patch(const Batch& bt, cudaStream_t st, int num_sms);  // tc_patch_kernel over the re-check queue
 // bitset_only: the adjacency did not come from launch_graph (tzr_max_clique on a caller's bitset): always popcount
 void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only = false);
 void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches);

@@ -35,13 +35,13 @@ def fixed_params(nb, **kw):
 # ------------------------------------------------------------------ tensor-core graph kernel
 @pytest.mark.parametrize("cfg,n", [("C2", 1500), ("C2cube", 1100), ("C3", 2000), ("C4", 640), ("C5", 1700), ("C2", 130)])
 def test_tc_kernel_is_used_and_bit_exact(ctx, cfg, n):
-    """Default path = tensor-core kernel (debug counter 7 counts the problems that took it); its bitset, degrees and
-    edge count equal the oracle's and the CUDA-core kernel's (flag 512), and the on-device verification of every decided
-    pair against the exact FP64 predicate (flag 2) finds no disagreement."""
+    """Tensor-core kernel (flag 1024; debug counter 7 counts the problems that took it): its bitset, degrees and edge
+    count equal the oracle's and the default CUDA-core kernel's, and the on-device verification of every decided pair
+    against the exact FP64 predicate (flag 2) finds no disagreement."""
     pr = synth.config_problem(cfg, 21, n=n)
     beta = 2 * pr["noise_bound"]
     obits, odeg, oe = orc.build_graph_bits(pr["src"], pr["dst"], pr["noise_bound"])
-    ctx.set_flags(2 | 4)
+    ctx.set_flags(1024 | 2 | 4)
     bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], beta)
     cnt = ctx.debug_counters()
     ctx.set_flags(0)
@@ -49,7 +49,7 @@ def test_tc_kernel_is_used_and_bit_exact(ctx, cfg, n):
     assert cnt["filter_mismatches"] == 0
     assert cnt["filter_rechecks"] < 0.01 * n * n + 64  # the exact path is the exception
     assert np.array_equal(bits, obits) and np.array_equal(deg, odeg) and ne == oe
-    ctx.set_flags(512 | 4)
+    ctx.set_flags(4)
     bits2, deg2, ne2 = ctx.graph_build(pr["src"], pr["dst"], beta)
     cnt2 = ctx.debug_counters()
     ctx.set_flags(0)
@@ -65,7 +65,7 @@ def test_tc_kernel_falls_back_when_ill_conditioned(ctx):
     dst[::7] += 300.0
     nb = 1e-5
     obits, _, oe = orc.build_graph_bits(src, dst, nb)
-    ctx.set_flags(2 | 4)
+    ctx.set_flags(1024 | 2 | 4)
     bits, _, ne = ctx.graph_build(src, dst, 2 * nb)
     cnt = ctx.debug_counters()
     ctx.set_flags(0)
@@ -84,7 +84,7 @@ def test_tc_kernel_duplicates_coincident_points(ctx):
         dst[k + 1] = dst[k]
         src[k + 1] = src[k] + 1e-9
     obits, odeg, oe = orc.build_graph_bits(src, dst, pr["noise_bound"])
-    ctx.set_flags(2 | 4)
+    ctx.set_flags(1024 | 2 | 4)
     bits, deg, ne = ctx.graph_build(src, dst, 2 * pr["noise_bound"])
     cnt = ctx.debug_counters()
     ctx.set_flags(0)
@@ -99,7 +99,7 @@ def test_tc_kernel_batch_mixed_with_fallback_problems(ctx):
     for b in (2, 5, 9):  # blow up the extent of these: they fall back
         prs[b]["dst"][::11] += 5e3
     p = capi.default_params(**fixed_params(prs[0]["noise_bound"]))
-    ctx.set_flags(4)
+    ctx.set_flags(1024 | 4)
     sols, cliques = ctx.solve_batch([q["src"] for q in prs], [q["dst"] for q in prs], p)
     cnt = ctx.debug_counters()
     ctx.set_flags(0)
@@ -115,7 +115,7 @@ def test_tc_kernel_unknown_scale(ctx):
     kw = fixed_params(pr["noise_bound"], estimate_scaling=1)
     src = pr["src"] * 1.7
     o = orc.solve(src, pr["dst"], orc.default_params(**kw))
-    ctx.set_flags(2 | 4)
+    ctx.set_flags(1024 | 2 | 4)
     g = ctx.solve(src, pr["dst"], capi.default_params(**kw))
     cnt = ctx.debug_counters()
     ctx.set_flags(0)
