@@ -266,7 +266,8 @@ int tzr_solve_batch_multi(const int32_t* devices, int n_devices, const tzr_param
  * bit 1 (2) = verify the FP32 / tensor-core filter against FP64 for every pair and count mismatches,
  * bit 2 (4) = count exact re-checks and clique search nodes, bit 8 (256) = degrees by a separate pass,
  * bit 10 (1024) = build the graph with the tensor-core kernel (tcgen05 Gram norms; bit-identical, measured slower than
- * the default CUDA-core kernel on B200: DESIGN.md 3.1), bit 9 (512) overrides it. */
+ * the default CUDA-core kernel on B200: DESIGN.md 3.1), bit 9 (512) overrides it, bit 11 (2048) = the one-MUFU
+ * CUDA-core variant (graph_strip3_kernel; bit-identical, FMA-pipe bound, 8 % slower). */
 int tzr_ctx_set_flags(tzr_ctx* ctx, uint32_t flags);
 int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx);
 /* Number of pairs of the most recent graph build that needed the exact FP64 re-check. */

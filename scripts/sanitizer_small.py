@@ -76,5 +76,18 @@ if "--no-cert" not in sys.argv:  # cuSOLVER's own kernels are slow under the san
     Wd = ctx.certifier_dual_projection(M0, th)
     r = ctx.certify(Rr, v1, v2, th, max_iterations=3)
     print("certify", mu, len(r["suboptimality_traj"]))
+# round 2: the tensor-core graph kernel (tcgen05 / TMA / mbarrier pipeline), the one-MUFU strip kernel, the re-check queue
+for flags in (1024, 1024 | 2, 2048, 2048 | 2, 2048 | 1):
+    ctx.set_flags(flags | 4)
+    for cfg, n in (("C2", 300), ("C2cube", 200)):
+        q = synth.config_problem(cfg, 3, n=n)
+        b3, d3, e3 = ctx.graph_build(q["src"], q["dst"], 2 * q["noise_bound"])
+        print("graph flags", flags, cfg, n, e3, ctx.debug_counters()["filter_mismatches"])
+    sols, cl = ctx.solve_batch_array(src[:9], dst[:9], capi.default_params(**dict(kw, noise_bound=prs[0]["noise_bound"])))
+    print("batch flags", flags, int(sols["valid"].sum()), "/ 9")
+ctx.set_flags(0)
+sols, cl = capi.solve_batch_multi([p["src"] for p in prs[:5]], [p["dst"] for p in prs[:5]],
+                                  capi.default_params(**dict(kw, noise_bound=prs[0]["noise_bound"])))
+print("multi", int(sols["valid"].sum()), "/ 5")
 ctx.close()
 print("DONE")

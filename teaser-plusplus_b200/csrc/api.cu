@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -96,6 +97,25 @@ int ensure_pinned(tzr_ctx* ctx, size_t bytes) {
   }
   ctx->h_pin_cap = bytes + bytes / 8 + 256;
   return TZR_OK;
+}
+
+// Copy `count` caller buffers of `per` bytes each into a contiguous pinned area with a few host threads (pageable
+// host memory cannot be DMA'd asynchronously; one thread moves ~10 GB/s, which is slower than the GPU consumes it).
+void parallel_stage(char* dst_base, const double* const* bufs, int first, int count, size_t per) {
+  const size_t total = per * (size_t)count;
+  int T = (int)std::min<size_t>(8, total / ((size_t)4 << 20));
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (hw && (unsigned)T > hw) T = (int)hw;
+  if (T <= 1) {
+    for (int b = 0; b < count; ++b) memcpy(dst_base + per * b, bufs[first + b], per);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([=] {
+      for (int b = t; b < count; b += T) memcpy(dst_base + per * b, bufs[first + b], per);
+    });
+  for (auto& x : th) x.join();
 }
 
 int next_pow2_host(int v) {
@@ -434,7 +454,7 @@ int run_pipeline(tzr_ctx* ctx, Batch& bt, const tzr_params& p, cudaEvent_t* ev, 
 // Run the pipeline chunk by chunk on the compute stream.  ready[c] (optional) is an event the chunk's inputs wait for.
 // bounds = n_chunks+1 ascending problem offsets (bounds[0] = 0, bounds[n_chunks] = B).
 int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<int>& bounds,
-                const cudaEvent_t* ready) {
+                const cudaEvent_t* ready, const std::function<int(int)>& before_chunk = nullptr) {
   const int n_chunks = (int)bounds.size() - 1;
   if (!ctx->stage_log) {
     ctx->graph_ev_used = 0;
@@ -462,6 +482,10 @@ int run_chunked(tzr_ctx* ctx, Batch& bt, const tzr_params& p, const std::vector<
     const int b0 = bounds[c], Bc = bounds[c + 1] - b0;
     cudaStream_t st = lanes ? ctx->hstream : ctx->stream;
     cudaStream_t sg = lanes ? ctx->gstream : ctx->stream;
+    if (before_chunk) {  // host-side work that produces this chunk's inputs (staging + H2D enqueue)
+      const int rcb = before_chunk(c);
+      if (rcb) return rcb;
+    }
     if (ready) {
       if (cudaStreamWaitEvent(sg, ready[c], 0) != cudaSuccess) return TZR_ERR_CUDA;
     }
@@ -881,11 +905,8 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
   }
   const double* hs = src[0];
   const double* hd = dst[0];
-  if (!(contiguous && pinned)) {
-    for (int b = 0; b < B; ++b) {
-      memcpy((char*)h_src + per * b, src[b], per);
-      memcpy((char*)h_dst + per * b, dst[b], per);
-    }
+  const bool staged = !(contiguous && pinned);  // stage through the context's pinned buffer, chunk by chunk (below)
+  if (staged) {
     hs = h_src;
     hd = h_dst;
   }
@@ -915,15 +936,24 @@ static int solve_uniform_host(tzr_ctx* ctx, const tzr_params* params, int B, int
     CK(cudaEventRecord(ctx->chunk_ev[n_chunks], st));
     CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[n_chunks], 0));
   }
-  for (int c = 0; c < n_chunks; ++c) {
+  // Per chunk, on the host: (staged inputs only) copy the chunk into the pinned area with a few threads, then enqueue its
+  // H2D copies; run_chunked enqueues the chunk's kernels right after, so the GPU works on chunk k while the host stages
+  // chunk k+1.
+  auto feed_chunk = [&](int c) -> int {
     const int b0 = bounds[c], Bc = bounds[c + 1] - b0;
-    CK(cudaMemcpyAsync((void*)(bt.src + (size_t)b0 * n * 3), (const char*)hs + per * b0, per * Bc,
-                       cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync((void*)(bt.dst + (size_t)b0 * n * 3), (const char*)hd + per * b0, per * Bc,
-                       cudaMemcpyHostToDevice, cs));
-    if (n_chunks > 1) CK(cudaEventRecord(ctx->chunk_ev[c], cs));
-  }
-  rc = run_chunked(ctx, bt, *params, bounds, n_chunks > 1 ? ctx->chunk_ev.data() : nullptr);
+    if (staged) {
+      parallel_stage((char*)h_src + per * b0, src, b0, Bc, per);
+      parallel_stage((char*)h_dst + per * b0, dst, b0, Bc, per);
+    }
+    if (cudaMemcpyAsync((void*)(bt.src + (size_t)b0 * n * 3), (const char*)hs + per * b0, per * Bc,
+                        cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+        cudaMemcpyAsync((void*)(bt.dst + (size_t)b0 * n * 3), (const char*)hd + per * b0, per * Bc,
+                        cudaMemcpyHostToDevice, cs) != cudaSuccess)
+      return TZR_ERR_CUDA;
+    if (n_chunks > 1 && cudaEventRecord(ctx->chunk_ev[c], cs) != cudaSuccess) return TZR_ERR_CUDA;
+    return TZR_OK;
+  };
+  rc = run_chunked(ctx, bt, *params, bounds, n_chunks > 1 ? ctx->chunk_ev.data() : nullptr, feed_chunk);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h_sol, bt.sol, (size_t)B * sizeof(tzr_solution), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip2_kernel
 }
 
 // ------------------------------------------------------------------------------------------------
-// graph strip kernel v7 (default): same decomposition, inputs and outputs as graph_strip2_kernel, cheaper pair test.
+// graph strip kernel v7 (debug flag 2048): same decomposition, inputs and outputs as graph_strip2_kernel, cheaper pair test.
 //   * one MUFU per pair instead of two: with t = a-b, s = a+b, q = sqrt(ab), w = s + 2q = (sqrt a + sqrt b)^2 the pair
 //     is an edge iff d = t^2 - beta^2 w <= 0 (d = w (g^2 - beta^2), g = |sqrt a - sqrt b|); both sides of the
 //     comparison are equal at the threshold, so the FP32 evaluation error is a few ulp of beta^2 w;
@@ -1055,11 +1055,12 @@ int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
   dim3 sgrid((unsigned)strip_grid(bt.n), (unsigned)bt.B);
   if (!bt.tc_active) cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);  // (launch_graph_tc zeroes it otherwise)
   bool v7 = false;
-  if (bt.flags_dbg & 2048u) {  // round-1 kernel (two MUFU, compares + ballots), A/B against the v7 default
+  if (bt.flags_dbg & 2048u) {  // v7 (one MUFU, sign-bit words, re-check queue): fewer instructions, but FMA-pipe bound
+    v7 = true;                 // on B200 and 8 % slower than the default (profiles/r02_graph_v7_vs_v6.md)
     if (bt.flags_dbg & 2u)
-      graph_strip2_kernel<true, 5, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
+      graph_strip3_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
     else
-      graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
+      graph_strip3_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
   }
 #ifdef TZR_AB_KERNELS
   else if (bt.flags_dbg & 16u)  // occupancy A/B: 6 CTAs/SM (80 registers)
@@ -1071,15 +1072,12 @@ int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
   else if (bt.flags_dbg & 128u)  // packed kernel at 6 CTAs/SM
     graph_strip2_kernel<false, 6, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
 #endif
+  else if (bt.flags_dbg & 2u)
+    graph_strip2_kernel<true, 5, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
   else if (bt.flags_dbg & 256u)  // degrees by the separate degree kernel (A/B against the fused default)
     graph_strip2_kernel<false, 8, false><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  else {
-    v7 = true;
-    if (bt.flags_dbg & 2u)
-      graph_strip3_kernel<true, 5><<<sgrid, kGraphThreads, 0, st>>>(bt);
-    else
-      graph_strip3_kernel<false, 8><<<sgrid, kGraphThreads, 0, st>>>(bt);
-  }
+  else  // default: packed FP32x2 strip kernel, 8 CTAs/SM, degrees fused
+    graph_strip2_kernel<false, 8, true><<<sgrid, kGraphThreads, 0, st>>>(bt);
   if (v7) {  // exact re-check of the pairs the strip kernel queued
     launch_graph_patch(bt, st, num_sms);
     ++launches;
@@ -1087,11 +1085,11 @@ int launch_graph(const Batch& bt0, cudaStream_t st, int num_sms) {
   return launches;
 }
 
-// fused degrees: the v7 default (also in verify mode) and the plain round-1 kernel
+// fused degrees: the default kernel (not its verify variant), and v7 always
 bool graph_fuses_degrees(const Batch& bt) {
   if (bt.flags_dbg & (8u | 16u | 32u | 64u | 128u | 256u)) return false;
-  if (bt.flags_dbg & 2048u) return (bt.flags_dbg & 2u) == 0;
-  return true;
+  if (bt.flags_dbg & 2048u) return true;
+  return (bt.flags_dbg & 2u) == 0;
 }
 
 void launch_degree(const Batch& bt, cudaStream_t st, bool bitset_only) {

@@ -57,6 +57,24 @@ def test_tc_kernel_is_used_and_bit_exact(ctx, cfg, n):
     assert np.array_equal(bits2, obits) and np.array_equal(deg2, odeg) and ne2 == oe
 
 
+@pytest.mark.parametrize("cfg,n", [("C2", 1300), ("C2cube", 1000), ("C3", 1500), ("C5", 900), ("C2", 33)])
+def test_v7_strip_kernel_bit_exact(ctx, cfg, n):
+    """graph_strip3_kernel (flag 2048: one MUFU per pair, sign-bit column words, re-check queue + tc_patch_kernel):
+    bit-identical to the oracle, every decided pair verified on the device, also with the exact-everything guard."""
+    pr = synth.config_problem(cfg, 5, n=n)
+    beta = 2 * pr["noise_bound"]
+    obits, odeg, oe = orc.build_graph_bits(pr["src"], pr["dst"], pr["noise_bound"])
+    for flags in (2048 | 2 | 4, 2048 | 4, 2048 | 1):
+        ctx.set_flags(flags)
+        bits, deg, ne = ctx.graph_build(pr["src"], pr["dst"], beta)
+        cnt = ctx.debug_counters()
+        ctx.set_flags(0)
+        assert cnt["filter_mismatches"] == 0
+        assert np.array_equal(bits, obits) and np.array_equal(deg, odeg) and ne == oe
+        if not flags & 1:
+            assert cnt["filter_rechecks"] < 0.01 * n * n + 64
+
+
 def test_tc_kernel_falls_back_when_ill_conditioned(ctx):
     """A noise bound that is tiny against the extent of the clouds (C1-like: beta/D ~ 1e-4) makes the tensor-core
     filter's undecided band wider than beta/4: prep_kernel routes the problem to the CUDA-core kernel; bits stay exact."""
