@@ -8,6 +8,7 @@
 quoted on.  All use fixed scale (what every reference example uses) unless --estimate-scaling is given.
     C1      bunny, N=1889, 1700 outlier draws (teaser_cpp_ply; README's 0.787 s datum)       single problem
     C2      N=5000, 95 % outliers, "ball" outlier model                                        batch/GPU, weak scaling
+    C2scale N=5000, 80 % outliers, ball, estimate_scaling=true                batch 16/GPU, weak scaling
     C2cube  N=5000, 95 % outliers, "in-cube" outliers (real branch-and-bound in the clique)   batch/GPU, weak scaling
     C3      N=10000, 99 % outliers, in-cube (max-clique stress)                                batch/GPU, weak scaling
     C4      4096 problems x N=2000, 90 % outliers, sharded b mod G                            fixed batch, strong scaling
@@ -42,6 +43,10 @@ CONFIGS = {
     # name: (synth cfg, n, default batch per GPU (weak) or total batch (strong), scaling, description)
     "C1": dict(n=1889, batch=1, scaling="weak", desc="C1 bunny: N=1889 correspondences, 1700 outlier draws (teaser_cpp_ply), nb=0.001"),
     "C2": dict(n=5000, batch=1024, scaling="weak", desc="C2: N=5000 correspondences, 95% outliers (ball)"),
+    "C2scale": dict(n=5000, batch=16, scaling="weak", estimate_scaling=True,
+                    desc="C2scale: N=5000 correspondences, 80% outliers (ball) — C2's geometry at the highest outlier ratio "
+                         "where the reference's TLS scale estimator still finds the scale with this outlier model (oracle: "
+                         "s_hat = 7.6 instead of 1 at 90 % and 95 %, the planted inliers are then lost by reference and GPU alike)"),
     "C2cube": dict(n=5000, batch=256, scaling="weak", desc="C2cube: N=5000 correspondences, 95% outliers (in-cube)"),
     "C3": dict(n=10000, batch=32, scaling="weak", desc="C3: N=10000 correspondences, 99% outliers (in-cube, max-clique stress)"),
     "C3ball": dict(n=10000, batch=64, scaling="weak", desc="C3ball: N=10000 correspondences, 99% outliers (ball)"),
@@ -224,6 +229,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-problems", type=int, default=16)
     args = ap.parse_args()
+    if CONFIGS[args.config].get("estimate_scaling"):
+        args.estimate_scaling = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -7,7 +7,7 @@ timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r02_pytest_gpu.log 2>
 for cfg in C2 C3 C2cube C4 C5 C1; do
   timeout 900 python bench.py --config $cfg --steps 10 --warmup 3 > gpurun_out/r02_bench_${cfg}.json 2> gpurun_out/r02_bench_${cfg}.err; echo "bench $cfg rc=$?"
 done
-timeout 900 python bench.py --config C2 --estimate-scaling --batch 16 --steps 3 --warmup 3 > gpurun_out/r02_bench_C2_estimate_scaling.json 2> gpurun_out/r02_bench_C2_estimate_scaling.err; echo "bench C2 scale rc=$?"
+timeout 900 python bench.py --config C2scale --steps 3 --warmup 3 > gpurun_out/r02_bench_C2scale.json 2> gpurun_out/r02_bench_C2scale.err; echo "bench C2scale rc=$?"
 timeout 600 python bench.py --impl reference --config C2 --steps 6 > gpurun_out/r02_bench_C2_reference_arm.json 2>/dev/null; echo "ref C2 rc=$?"
 timeout 600 python bench.py --impl reference --config C1 --steps 10 > gpurun_out/r02_bench_C1_reference_arm.json 2>/dev/null; echo "ref C1 rc=$?"
 python - <<'PY'

@@ -174,20 +174,29 @@ int setup_batch(tzr_ctx* ctx, int B, int n, bool own_points, Batch* out, bool co
   ENS(flg, (size_t)B * sizeof(int32_t));
   ENS(kfinal, (size_t)B * sizeof(int32_t));
   ENS(tstart, (size_t)B * sizeof(unsigned long long));
-  // exact phase geometry: ~2 CTAs per SM over the whole batch, at least 1 CTA per problem
-  int G = (2 * ctx->num_sms + B - 1) / B;
-  if (G < 1) G = 1;
-  if (G > 2 * ctx->num_sms) G = 2 * ctx->num_sms;
-  const size_t warps = (size_t)B * G * 8;
+  // exact phase geometry: a persistent grid that fills the GPU; its warps own the search scratch (any problem)
+  int G = clique_exact_grid(n, ctx->num_sms);
+  {
+    const long long roots = ((long long)B * n + 7) / 8;  // never more warps than root vertices
+    if ((long long)G > roots) G = (int)std::max<long long>(1, roots);
+  }
+  const size_t warps = (size_t)G * 8;
   const size_t level_bytes = (size_t)2 * W32 * sizeof(uint32_t);
-  size_t depth = ((size_t)1 << 30) / (warps * level_bytes);
+  size_t depth = ((size_t)4 << 30) / (warps * level_bytes);
   if (depth > 512) depth = 512;
   if (depth > (size_t)n) depth = (size_t)n;
   if (depth < 16) depth = 16;
   bt.exact_ctas = G;
   bt.max_depth = (int)depth;
+  {
+    // problems under search at a time: their bitsets should stay in the L2 together (~48 MB of the 126 MB: the
+    // stacks, the other lane's graph kernel and the two L2 partitions take the rest)
+    const size_t bits = n * W32 * sizeof(uint32_t);
+    const size_t conc = ((size_t)48 << 20) / std::max<size_t>(bits, 1);
+    bt.exact_conc = (int)std::min<size_t>(std::max<size_t>(conc, 1), (size_t)B);
+  }
   ENS(stack, warps * depth * level_bytes);
-  ENS(cv, warps * (size_t)n * sizeof(int32_t));
+  ENS(cv, std::max(warps, (size_t)4 * B) * (size_t)n * sizeof(int32_t));
   ENS(centry, warps * depth * sizeof(int32_t));
   bt.sort_cap = next_pow2_host(2 * n);
   ENS(ps, Bn * 3 * sizeof(double));
@@ -290,7 +299,6 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
   Batch s = bt;
   const size_t n = (size_t)bt.n, o = (size_t)b0;
   const size_t W32 = (size_t)pitch32(bt.n);
-  const size_t warps = (size_t)bt.exact_ctas * 8;
   s.B = Bc;
   s.src = bt.src + o * n * 3;
   s.dst = bt.dst + o * n * 3;
@@ -314,9 +322,6 @@ Batch sub_batch(const Batch& bt, int b0, int Bc) {
   s.flags = bt.flags + o;
   s.kcore_final = bt.kcore_final + o;
   s.t_start = bt.t_start + o;
-  s.stack = bt.stack + o * warps * (size_t)bt.max_depth * 2 * W32;
-  s.cv = bt.cv + o * warps * n;
-  s.centry = bt.centry + o * warps * (size_t)bt.max_depth;
   s.ps = bt.ps + o * n * 3;
   s.pd = bt.pd + o * n * 3;
   s.wgt = bt.wgt + o * (size_t)bt.rot_cap;

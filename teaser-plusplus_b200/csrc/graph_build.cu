@@ -945,6 +945,8 @@ __global__ void __launch_bounds__(kGraphThreads, kMinBlocks) graph_strip3_kernel
       base = __shfl_sync(0xffffffffu, base, 0);
       const bool queued = base + (unsigned int)total <= bt.tc_list_cap;
       unsigned int pos = base + (unsigned int)(incl - nflag);
+      if (!queued)  // the first warp that does not fit leaves [base, cap) unwritten: void entries for the patch kernel
+        for (unsigned int q = base + (unsigned int)lane; q < bt.tc_list_cap; q += 32u) bt.tc_list[q] = make_uint2(0xffffffffu, 0u);
       int nre = 0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {

@@ -499,6 +499,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
               bt.tc_list[pos++] = make_uint2((unsigned int)b, ((unsigned int)i << 16) | (unsigned int)(j0 + k));
             }
           } else {  // queue full (the count keeps growing; the patch kernel clamps it): exact evaluation in place
+            // the first warp that does not fit leaves [base, cap) unwritten: void entries (b = ~0) for the patch kernel
+            for (unsigned int q = base + (unsigned int)lane; q < bt.tc_list_cap; q += 32u) bt.tc_list[q] = make_uint2(0xffffffffu, 0u);
             int nre = 0;
             while (fmask) {
               const int k = __ffs(fmask) - 1;
@@ -553,6 +555,7 @@ __global__ void __launch_bounds__(256) tc_patch_kernel(Batch bt) {
   const bool scale_mode = bt.scale_mode != 0;
   for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
     const uint2 ent = bt.tc_list[e];
+    if (ent.x == 0xffffffffu) continue;  // gap left by the first warp that found the queue full
     const int b = (int)ent.x, i = (int)(ent.y >> 16), j = (int)(ent.y & 0xffffu);
     const double* src = bt.src + (size_t)b * n * 3;
     const double* dst = bt.dst + (size_t)b * n * 3;

@@ -36,6 +36,7 @@ constexpr int kHeurThreads = 512;
 constexpr int kPeelThreads = 1024;
 constexpr int kExactThreads = 256;
 constexpr int kExactWarps = kExactThreads / 32;
+constexpr int kSpecCand = 8;  // colouring: candidates resolved per round trip to the bitset (see node_colour)
 
 __device__ __forceinline__ const uint32_t* adj_row32(const Batch& bt, int b, int v) {
   return reinterpret_cast<const uint32_t*>(bt.adj) + ((size_t)b * bt.n + v) * pitch32(bt.n);
@@ -678,13 +679,13 @@ __global__ void __launch_bounds__(kPeelThreads) clique_kcore_kernel(Batch bt, do
 // K3: exact branch and bound, one warp per root.
 // dynamic smem per warp: Pc[W] | Q[W] | R[W] | Bs[W]
 // =================================================================================================
-size_t clique_exact_smem(int n) { return (size_t)pitch32(n) * 4 * 4 * kExactWarps + 16; }
+size_t clique_exact_smem(int n) { return ((size_t)pitch32(n) * 4 + kSpecCand) * 4 * kExactWarps + 16; }
 
 namespace {
 
-__device__ __forceinline__ int warp_popc(const uint32_t* bits, int W, int lane) {
+__device__ __forceinline__ int warp_popc(const uint32_t* bits, int W, int lane, int xlo = 0) {
   int c = 0;
-  for (int x = lane; x < W; x += 32) c += __popc(bits[x]);
+  for (int x = xlo + lane; x < W; x += 32) c += __popc(bits[x]);
   return __reduce_add_sync(0xffffffffu, c);
 }
 
@@ -709,7 +710,8 @@ struct WarpCtx {
   unsigned long long* cnt;  // debug counters (nullptr unless debug flag 4): see tzr_ctx_debug_counters
   const Batch* bt;
   int b, n, W, lane;
-  uint32_t *Pc, *Q, *R, *Bs;     // shared memory (this warp)
+  uint32_t *Pc, *Q, *R, *Bs;     // shared memory (this warp); words below xlo are never read nor written
+  int* cand;                     // shared memory (this warp): kSpecCand candidate vertices of the colouring
   uint32_t* stack;               // global: level d -> P at stack + d*2W, B at stack + d*2W + W
   int32_t* cv;                   // global: current clique
   int32_t* centry;               // global: clique size at entry of level d
@@ -723,7 +725,7 @@ struct WarpCtx {
 __device__ int node_reduce(WarpCtx& c, int& csz) {
   const int W = c.W, lane = c.lane;
   for (int round = 0; round < 8; ++round) {
-    const int cnt = warp_popc(c.Pc, W, lane);
+    const int cnt = warp_popc(c.Pc, W, lane, c.xlo);
     if (c.cnt && lane == 0) {
       atomicAdd(c.cnt + 3, 1ull);
       atomicAdd(c.cnt + 4, (unsigned long long)cnt);
@@ -732,7 +734,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     if (csz + cnt < Lc) return 0;  // cannot even tie the incumbent (ties are enumerated: canonical result)
     if (cnt == 0) return 1;
     const int need = Lc - csz - 1;  // a candidate must have >= need neighbours inside P to reach size Lc
-    for (int x = lane; x < W; x += 32) c.Q[x] = c.Pc[x];
+    for (int x = c.xlo + lane; x < W; x += 32) c.Q[x] = c.Pc[x];
     __syncwarp();
     bool changed = false;
     int added = 0;
@@ -767,7 +769,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
       }
     }
     __syncwarp();
-    for (int x = lane; x < W; x += 32) c.Pc[x] = c.Q[x];
+    for (int x = c.xlo + lane; x < W; x += 32) c.Pc[x] = c.Q[x];
     __syncwarp();
     csz += added;
     if (!changed) {
@@ -778,52 +780,121 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
       return 2;
     }
   }
-  const int cnt = warp_popc(c.Pc, W, lane);
+  const int cnt = warp_popc(c.Pc, W, lane, c.xlo);
   if (csz + cnt < *c.Lp + c.strict) return 0;
   if (cnt == 0) return 1;
   return 2;
 }
 
-// Greedy sequential colouring of Pc; Bs = vertices whose colour >= kmin.  Returns |Bs|.
+// Greedy sequential colouring of Pc (classes in index order); Bs = vertices whose colour >= kmin.  Returns |Bs|.
+//
+// A class is the greedy maximal independent set of the uncoloured vertices: take the lowest vertex u of the residual R,
+// R &= ~N(u), repeat.  One pick per round trip to the L2-resident bitset would make the warp latency-bound, so up to
+// kSpecCand lowest vertices of R are resolved per round trip: (1) the k(k-1)/2 adjacency bits among them are fetched
+// by as many lanes at once and the sequential greedy rule is replayed on that little matrix in registers — the
+// accepted candidates are exactly the picks the one-at-a-time loop would make, because the lowest vertex of R & ~N(u0)
+// is the first candidate not adjacent to u0, and so on; (2) the rows of the accepted candidates are read together
+// (independent loads), each only from its own word upwards: bits of R below a pick are already decided.
 __device__ int node_colour(WarpCtx& c, int csz) {
-  const int W = c.W, lane = c.lane;
+  const int W = c.W, lane = c.lane, xlo = c.xlo;
   int kmin = *c.Lp + c.strict - csz;  // colour k bounds cliques by k: need csz + k >= L to tie or beat
   if (kmin < 1) kmin = 1;
-  for (int x = lane; x < W; x += 32) {
+  for (int x = xlo + lane; x < W; x += 32) {
     c.Q[x] = c.Pc[x];
     c.Bs[x] = 0u;
   }
   __syncwarp();
-  const int warp_popc_lane0_hint = c.cnt ? warp_popc(c.Pc, W, lane) : 0;
-  int nB = 0;
-  int qstart = 0;
-  if (c.cnt && lane == 0) {
-    atomicAdd(c.cnt + 5, 1ull);
-    atomicAdd(c.cnt + 6, (unsigned long long)warp_popc_lane0_hint);
+  if (c.cnt) {
+    const int np = warp_popc(c.Pc, W, lane, xlo);
+    if (lane == 0) {
+      atomicAdd(c.cnt + 5, 1ull);
+      atomicAdd(c.cnt + 6, (unsigned long long)np);
+    }
   }
+  // pair (i, j), i < j < kSpecCand, handled by this lane in step (1): p = j(j-1)/2 + i
+  int pi = 0, pj = 1;
+  {
+    int base = 0;
+    while (base + pj <= lane) {
+      base += pj;
+      ++pj;
+    }
+    pi = lane - base;
+  }
+  int nB = 0;
+  int qstart = xlo;
   for (int k = 1;; ++k) {
     // anything left uncoloured?
     int xq;
     const int first = warp_first_bit(c.Q, W, lane, qstart, &xq);
     if (first < 0) break;
     qstart = xq;
-    for (int x = lane; x < W; x += 32) c.R[x] = c.Q[x];
+    for (int x = qstart + lane; x < W; x += 32) c.R[x] = c.Q[x];
     __syncwarp();
     int xr = qstart;
-    while (true) {
-      int xf;
-      const int u = warp_first_bit(c.R, W, lane, xr, &xf);
-      if (u < 0) break;
-      xr = xf;
-      const uint32_t* ru = adj_row32(*c.bt, c.b, u);
-      for (int y = lane; y < W; y += 32) c.R[y] &= ~ru[y];
-      __syncwarp();
-      if (lane == 0) {
-        c.R[u >> 5] &= ~(1u << (u & 31));
-        c.Q[u >> 5] &= ~(1u << (u & 31));
-        if (k >= kmin) c.Bs[u >> 5] |= 1u << (u & 31);
+    while (xr < W) {
+      // ---- the lowest <= kSpecCand vertices of R inside the 32-word window at xr
+      const int x = xr + lane;
+      const uint32_t w = x < W ? c.R[x] : 0u;
+      const int pc = __popc(w);
+      int incl = pc;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
       }
-      if (k >= kmin) ++nB;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) {
+        xr += 32;
+        continue;
+      }
+      {
+        int rank = incl - pc;
+        uint32_t ww = w;
+        while (ww && rank < kSpecCand) {
+          c.cand[rank++] = x * 32 + __ffs(ww) - 1;
+          ww &= ww - 1;
+        }
+      }
+      __syncwarp();
+      const int nc = total < kSpecCand ? total : kSpecCand;
+      const int xlast = c.cand[nc - 1] >> 5;
+      int u[kSpecCand];
+#pragma unroll
+      for (int q = 0; q < kSpecCand; ++q) u[q] = c.cand[q < nc ? q : 0];
+      // ---- (1) adjacency among the candidates, greedy rule replayed in registers
+      bool e = false;
+      if (lane < kSpecCand * (kSpecCand - 1) / 2 && pj < nc) {
+        const int ui = c.cand[pi], uj = c.cand[pj];
+        e = (adj_row32(*c.bt, c.b, ui)[uj >> 5] >> (uj & 31)) & 1u;
+      }
+      const unsigned em = __ballot_sync(0xffffffffu, e);
+      unsigned acc = 1u;
+#pragma unroll
+      for (int j = 1; j < kSpecCand; ++j) {
+        const unsigned col = (em >> (j * (j - 1) / 2)) & ((1u << j) - 1u);  // bit i: candidate i adjacent to j
+        if (j < nc && !(col & acc)) acc |= 1u << j;
+      }
+      // ---- (2) R &= ~(union of the accepted rows), each row from its own word upwards
+      const uint32_t* r[kSpecCand];
+#pragma unroll
+      for (int q = 0; q < kSpecCand; ++q) r[q] = adj_row32(*c.bt, c.b, u[q]);
+      for (int y = (u[0] >> 5) + lane; y < W; y += 32) {
+        uint32_t m = 0u;
+#pragma unroll
+        for (int q = 0; q < kSpecCand; ++q)
+          if (((acc >> q) & 1u) && y >= (u[q] >> 5)) m |= r[q][y];
+        c.R[y] &= ~m;
+      }
+      __syncwarp();
+      if (lane < nc && ((acc >> lane) & 1u)) {
+        const int ul = c.cand[lane];
+        const uint32_t bit = 1u << (ul & 31);
+        atomicAnd(&c.R[ul >> 5], ~bit);
+        atomicAnd(&c.Q[ul >> 5], ~bit);
+        if (k >= kmin) atomicOr(&c.Bs[ul >> 5], bit);
+      }
+      if (k >= kmin) nB += __popc(acc);
+      xr = xlast;  // everything below the last candidate is decided
       __syncwarp();
     }
   }
@@ -883,30 +954,10 @@ __device__ void record_clique(WarpCtx& c, int csz) {
   __syncwarp();
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
-  const int b = blockIdx.y;
-  if (bt.alive_cnt[b] == 0) return;
-  const int n = bt.n, W = pitch32(n);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* wbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * 4 * W;
-  WarpCtx c;
-  c.cnt = (bt.flags_dbg & 4u) ? bt.mismatches : nullptr;
-  c.bt = &bt;
+// Branch and bound below one root vertex after another of problem b, until its root counter runs out.
+__device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
+  const int n = bt.n, W = c.W, lane = c.lane;
   c.b = b;
-  c.n = n;
-  c.W = W;
-  c.lane = lane;
-  c.Pc = wbase;
-  c.Q = wbase + W;
-  c.R = wbase + 2 * W;
-  c.Bs = wbase + 3 * W;
-  const size_t gw = ((size_t)b * gridDim.x + blockIdx.x) * kExactWarps + wid;  // global warp slot
-  c.stack = bt.stack + gw * (size_t)bt.max_depth * 2 * W;
-  c.cv = bt.cv + gw * (size_t)n;
-  c.centry = bt.centry + gw * (size_t)bt.max_depth;
   c.Lp = bt.L + b;
   c.strict = (bt.flags[b] & 8) ? 1 : 0;
   const int ub_stop = c.strict ? (bt.flags[b] >> 8) : 0x7fffffff;  // LP bound of the NT step: reaching it ends the search
@@ -933,23 +984,23 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
     if (bt.flags[b] & 2) break;  // deadline hit elsewhere
     if (*c.Lp >= ub_stop) break;
     // root node: P = N(v) ∩ alive ∩ {u > v}
+    c.xlo = v >> 5;
     {
       const uint32_t* rv = adj_row32(bt, b, v);
       const int xv = v >> 5;
-      for (int x = lane; x < W; x += 32) {
+      for (int x = xv + lane; x < W; x += 32) {
         uint32_t m = rv[x] & alive[x];
-        if (x < xv) m = 0u;
-        else if (x == xv) m &= ~((2u << (v & 31)) - 1u);  // keep bits strictly above v ((2<<31)-1 wraps to all ones)
+        if (x == xv) m &= ~((2u << (v & 31)) - 1u);  // keep bits strictly above v ((2<<31)-1 wraps to all ones)
         c.Pc[x] = m;
       }
       __syncwarp();
     }
     if (lane == 0) c.cv[0] = v;
-    c.xlo = v >> 5;
     __syncwarp();
     int csz = 1;
     int depth = 0;  // number of saved levels
     bool fresh = true;
+    bool at_root = true;
     while (true) {
       if (fresh) {
         // ---- process the node in Pc
@@ -963,7 +1014,16 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
           break;
         }
         if (c.cnt && lane == 0) atomicAdd(c.cnt + 2, 1ull);
-        const int r = node_reduce(c, csz);
+        int r = 2;
+        if (at_root) {
+          // Most roots fall to the colour bound at once (an outlier's later neighbourhood holds no clique anywhere near
+          // the incumbent): try it before paying the same number of row reads for the degree rules.
+          const int cnt = warp_popc(c.Pc, W, lane, c.xlo);
+          if (csz + cnt < *c.Lp + c.strict) r = 0;
+          else if (cnt > 0 && node_colour(c, csz) == 0) r = 0;
+          at_root = false;
+        }
+        if (r) r = node_reduce(c, csz);
         if (r == 1) {
           if (csz >= *c.Lp + c.strict) record_clique(c, csz);
         } else if (r == 2) {
@@ -973,7 +1033,7 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
               if (lane == 0) atomicOr(bt.flags + b, 1);
             } else {
               uint32_t* Pd = c.stack + (size_t)depth * 2 * W;
-              for (int x = lane; x < W; x += 32) {
+              for (int x = c.xlo + lane; x < W; x += 32) {
                 Pd[x] = c.Pc[x];
                 Pd[W + x] = c.Bs[x];
               }
@@ -993,9 +1053,9 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
       const int ce = c.centry[d];
       int xf;
       // cheap level bound: every remaining clique of this level has size <= ce + |P_d| (ties still explored)
-      const int cntP = warp_popc(Pd, W, lane);
+      const int cntP = warp_popc(Pd, W, lane, c.xlo);
       int u = -1;
-      if (ce + cntP >= *c.Lp + c.strict) u = warp_first_bit(Bd, W, lane, 0, &xf);
+      if (ce + cntP >= *c.Lp + c.strict) u = warp_first_bit(Bd, W, lane, c.xlo, &xf);
       if (u < 0) {
         --depth;
         continue;
@@ -1008,10 +1068,61 @@ __global__ void __launch_bounds__(kExactThreads) clique_exact_kernel(Batch bt) {
       }
       __syncwarp();
       const uint32_t* ru = adj_row32(bt, b, u);
-      for (int x = lane; x < W; x += 32) c.Pc[x] = Pd[x] & ru[x];
+      for (int x = c.xlo + lane; x < W; x += 32) c.Pc[x] = Pd[x] & ru[x];
       __syncwarp();
       csz = ce + 1;
       fresh = true;
+    }
+  }
+}
+
+}  // namespace
+
+// Persistent grid (as many CTAs as fit the GPU), every warp on its own: it sweeps the problems of the batch once,
+// starting at one of `exact_conc` evenly spaced problems, and on each problem that still has roots takes root vertices
+// from that problem's counter until they run out.  All warps of a start group therefore work on the same problem and
+// move on together: at most ~exact_conc adjacency bitsets are live at a time, chosen on the host so that they fit the
+// L2 (one 10k-vertex bitset is 12.5 MB; a chunk of eight of them under search at once ran at HBM speed, ~2.7x slower
+// per problem than one at a time).  Scratch (stack, clique, entry sizes) belongs to the warp, not to the problem.
+__global__ void __launch_bounds__(kExactThreads, 3) clique_exact_kernel(Batch bt) {
+  const int n = bt.n, W = pitch32(n), B = bt.B;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * (4 * W + kSpecCand);
+  WarpCtx c;
+  c.cnt = (bt.flags_dbg & 4u) ? bt.mismatches : nullptr;
+  c.bt = &bt;
+  c.b = 0;
+  c.n = n;
+  c.W = W;
+  c.lane = lane;
+  c.Pc = wbase;
+  c.Q = wbase + W;
+  c.R = wbase + 2 * W;
+  c.Bs = wbase + 3 * W;
+  c.cand = reinterpret_cast<int*>(wbase + 4 * W);
+  const size_t gw = (size_t)blockIdx.x * kExactWarps + wid;  // this warp's scratch slot
+  c.stack = bt.stack + gw * (size_t)bt.max_depth * 2 * W;
+  c.cv = bt.cv + gw * (size_t)n;
+  c.centry = bt.centry + gw * (size_t)bt.max_depth;
+  c.Lp = bt.L;
+  c.strict = 0;
+  c.xlo = 0;
+  const int nstart = bt.exact_conc < 1 ? 1 : (bt.exact_conc > B ? B : bt.exact_conc);
+  // the warps of a CTA share a start problem; the start groups are interleaved over the grid (and so over the SMs)
+  const int bstart = (int)((long long)(blockIdx.x % nstart) * B / nstart);
+  const volatile int32_t* rc = bt.root_ctr;
+  for (int off = 0; off < B; off += 32) {
+    int bb = bstart + off + lane;
+    if (bb >= B) bb -= B;
+    const bool act = (off + lane < B) && bt.alive_cnt[bb] != 0 && rc[bb] < n && !(bt.flags[bb] & 2);
+    unsigned m = __ballot_sync(0xffffffffu, act);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      int b = bstart + off + l;
+      if (b >= B) b -= B;
+      exact_search_problem(bt, c, b);
     }
   }
 }
@@ -1047,7 +1158,7 @@ __global__ void __launch_bounds__(32) clique_lp_kernel(Batch bt) {
   for (int x = lane; x < W; x += 32) cntA += __popc(A[x]);
   for (int o = 16; o; o >>= 1) cntA += __shfl_xor_sync(0xffffffffu, cntA, o);
   if (2 * L < cntA) return;  // far from a clique: the LP bound cannot close such a gap
-  int32_t* base = bt.cv + (size_t)b * bt.exact_ctas * kExactWarps * (size_t)n;
+  int32_t* base = bt.cv + (size_t)b * 4 * (size_t)n;  // cv holds max(search warps, 4 B) rows of n: free between the passes
   int32_t *mateL = base, *mateR = base + n, *parent = base + 2 * (size_t)n, *queue = base + 3 * (size_t)n;
   for (int v = lane; v < n; v += 32) {
     mateL[v] = -1;
@@ -1221,8 +1332,8 @@ __global__ void clique_resume_kernel(Batch bt) {
   }
 }
 
-void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches) {
-  const int n = bt.n;
+namespace {
+void clique_set_attrs() {
   // per device: a process may hold contexts on several GPUs
   static bool attr_done_dev[64] = {};
   int dev = 0;
@@ -1235,6 +1346,22 @@ void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t 
     cudaFuncSetAttribute(clique_kcore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
+}
+}  // namespace
+
+int clique_exact_grid(int n, int num_sms) {
+  clique_set_attrs();
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clique_exact_kernel, kExactThreads, clique_exact_smem(n)) !=
+          cudaSuccess ||
+      occ < 1)
+    occ = 1;
+  return occ * num_sms;
+}
+
+void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t st, int* n_launches) {
+  const int n = bt.n;
+  clique_set_attrs();
   int launches = 0;
   Batch b2 = bt;
   if (mode == 2) {  // KCORE_HEU (graph.cc:66-81)
@@ -1252,7 +1379,7 @@ void launch_clique(const Batch& bt, const tzr_params& p, int mode, cudaStream_t 
     // Nemhauser–Trotter bound / reduction for whatever ran into that deadline, then the rest of the caller's budget.
     constexpr unsigned long long kFirstPassNs = 50ull * 1000 * 1000;
     const unsigned long long total = bt.budget_ns;  // 0 = unlimited
-    dim3 g3((unsigned)bt.exact_ctas, (unsigned)bt.B);
+    const unsigned g3 = (unsigned)bt.exact_ctas;
     Batch p1 = b2;
     p1.budget_ns = (total == 0ull || total > kFirstPassNs) ? kFirstPassNs : total;
     clique_exact_kernel<<<g3, kExactThreads, clique_exact_smem(n), st>>>(p1);

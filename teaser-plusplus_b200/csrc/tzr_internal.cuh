@@ -90,7 +90,8 @@ struct Batch {
   int32_t* cv;            // per warp: n ints (current clique)
   int32_t* centry;        // per warp: max_depth ints
   int max_depth;
-  int exact_ctas;         // CTAs per problem in the exact phase
+  int exact_ctas;         // CTAs of the (persistent) exact-phase grid; scratch above is per warp of that grid
+  int exact_conc;         // problems searched at a time (bitsets that fit the L2 together)
   // rotation / translation scratch (per problem)
   double* ps;             // B*3*n chain TIMs src
   double* pd;             // B*3*n chain TIMs dst (de-scaled)
@@ -162,6 +163,7 @@ void launch_rot_trans(const Batch& bt, const tzr_params& p, int use_clique, cuda
 size_t clique_heur_smem(int n);
 size_t clique_peel_smem(int n);
 size_t clique_exact_smem(int n);
+int clique_exact_grid(int n, int num_sms);  // CTAs of the persistent exact-phase grid on the current device
 
 // stand-alone stage helpers used by the per-stage C-ABI entry points
 void launch_gnc_only(int alg, const double* src, const double* dst, int m, double noise_bound, double gnc_factor,

@@ -80,6 +80,9 @@ def config_problem(cfg: str, b: int = 0, n: int | None = None):
     if cfg == "C2":
         n = n or 5000
         return make_problem(n, 0.95, 5000 * 1000 + b, "ball")
+    if cfg == "C2scale":  # the unknown-scale line: see bench.py CONFIGS for why 80 %
+        n = n or 5000
+        return make_problem(n, 0.80, 5000 * 1000 + b, "ball")
     if cfg == "C2cube":
         n = n or 5000
         return make_problem(n, 0.95, 5000 * 1000 + b, "incube")
