@@ -232,7 +232,12 @@ class Context:
         self._ck(lib().tzr_ctx_debug_counters(self._h, _p(out, C.c_int64)))
         return dict(filter_mismatches=int(out[0]), filter_rechecks=int(out[1]), clique_nodes=int(out[2]),
                     reduce_rounds=int(out[3]), reduce_vertices=int(out[4]), colourings=int(out[5]),
-                    coloured_vertices=int(out[6]), tc_problems=int(out[7]))
+                    coloured_vertices=int(out[6]), tc_problems=int(out[7]),
+                    # exact clique search, per-root timing (flag 4): cycles in the root colour bound / degree rules /
+                    # colourings, slowest root (ns, vertex), summed root time, roots above 1 ms
+                    root_colour_cycles=int(out[8]), reduce_cycles=int(out[9]), colour_cycles=int(out[10]),
+                    slowest_root_ns=int(out[11]) >> 16, slowest_root_vertex=int(out[11]) & 0xffff,
+                    root_ns_total=int(out[12]), roots_over_1ms=int(out[13]))
 
     def kernel_launches(self) -> int:
         return int(lib().tzr_ctx_kernel_launches(self._h))

@@ -1001,6 +1001,8 @@ __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
     int depth = 0;  // number of saved levels
     bool fresh = true;
     bool at_root = true;
+    const unsigned long long t_root = c.cnt ? globaltimer_ns() : 0ull;  // debug flag 4: per-root wall time
+    long long ck_first = 0, ck_reduce = 0, ck_colour = 0;                // and cycles per phase
     while (true) {
       if (fresh) {
         // ---- process the node in Pc
@@ -1015,6 +1017,7 @@ __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
         }
         if (c.cnt && lane == 0) atomicAdd(c.cnt + 2, 1ull);
         int r = 2;
+        long long ck0 = c.cnt ? clock64() : 0ll;
         if (at_root) {
           // Most roots fall to the colour bound at once (an outlier's later neighbourhood holds no clique anywhere near
           // the incumbent): try it before paying the same number of row reads for the degree rules.
@@ -1022,12 +1025,23 @@ __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
           if (csz + cnt < *c.Lp + c.strict) r = 0;
           else if (cnt > 0 && node_colour(c, csz) == 0) r = 0;
           at_root = false;
+          if (c.cnt) {
+            const long long ck1 = clock64();
+            ck_first += ck1 - ck0;
+            ck0 = ck1;
+          }
         }
         if (r) r = node_reduce(c, csz);
+        if (c.cnt) {
+          const long long ck1 = clock64();
+          ck_reduce += ck1 - ck0;
+          ck0 = ck1;
+        }
         if (r == 1) {
           if (csz >= *c.Lp + c.strict) record_clique(c, csz);
         } else if (r == 2) {
           const int nB = node_colour(c, csz);
+          if (c.cnt) ck_colour += clock64() - ck0;
           if (nB > 0) {
             if (depth >= bt.max_depth) {
               if (lane == 0) atomicOr(bt.flags + b, 1);
@@ -1072,6 +1086,15 @@ __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
       __syncwarp();
       csz = ce + 1;
       fresh = true;
+    }
+    if (c.cnt && lane == 0) {
+      const unsigned long long dt = globaltimer_ns() - t_root;
+      atomicAdd(c.cnt + 8, (unsigned long long)ck_first);
+      atomicAdd(c.cnt + 9, (unsigned long long)ck_reduce);
+      atomicAdd(c.cnt + 10, (unsigned long long)ck_colour);
+      atomicMax(c.cnt + 11, (dt << 16) | (unsigned long long)(v & 0xffff));  // slowest root: ns << 16 | vertex
+      atomicAdd(c.cnt + 12, dt);
+      if (dt > 1000000ull) atomicAdd(c.cnt + 13, 1ull);  // roots that took more than 1 ms
     }
   }
 }
