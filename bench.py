@@ -469,9 +469,10 @@ def main():
                           "sequential sweep), inlier graph identical except pairs whose predicate margin is below the "
                           "scale difference (tests/test_gpu_parity.py::test_unknown_scale_large_n); n <= 256: bit-exact"}
         # rotation / translation error vs the oracle on identical inputs (metric's second half) + CPU baseline
-        if not args.no_cpu_baseline:
+        if args.parity_problems > 0 or not args.no_cpu_baseline:
             import oracle_lib as orc
             threads = oracle_threads(orc, os.cpu_count() or 1)
+        if args.parity_problems > 0:
             errs, t_par = [], time.perf_counter()
             for b in range(min(B, args.parity_problems)):
                 o = orc.solve(src_h[b], dst_h[b], solver_params(orc, cfg, nb, args.estimate_scaling))
@@ -485,6 +486,7 @@ def main():
                                            "trans_err_m_max": max(e[1] for e in errs),
                                            "scale_err_max": max(e[3] for e in errs),
                                            "clique_identical": all(e[2] for e in errs), "problems": len(errs)}
+        if not args.no_cpu_baseline:
             if world == 1:
                 s = cpu_sample(cfg, args.estimate_scaling, synth, 777, 24, 20.0, threads)
                 line["cpu_baseline"] = {"value": s["value"], "unit": "registrations/s", "cores": s["cores"], "kind": "port",

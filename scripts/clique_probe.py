@@ -6,13 +6,16 @@ sys.path.insert(0, ".")
 capi = importlib.import_module("teaser-plusplus_b200.capi")
 synth = importlib.import_module("teaser-plusplus_b200.synth")
 
+import os
+EXTRA = int(os.environ.get("PROBE_FLAGS", "0"))   # 4096: no block bound, 8192: no singleton path
+NPROB = int(os.environ.get("PROBE_PROBLEMS", "3"))
 ctx = capi.Context()
 for cfg in (sys.argv[1:] or ["C3", "C2cube", "C5"]):
-    for b in range(3):
+    for b in range(NPROB):
         pr = synth.config_problem(cfg, b)
         p = capi.default_params(noise_bound=pr["noise_bound"], estimate_scaling=0, rotation_cost_threshold=1e-12)
         ctx.solve(pr["src"], pr["dst"], p)              # warm (allocations)
-        ctx.set_flags(4)
+        ctx.set_flags(4 | EXTRA)
         t0 = time.perf_counter()
         r = ctx.solve(pr["src"], pr["dst"], p)
         dt = (time.perf_counter() - t0) * 1e3
@@ -27,4 +30,5 @@ for cfg in (sys.argv[1:] or ["C3", "C2cube", "C5"]):
               "reduce rounds", c["reduce_rounds"], "reduce vertices", c["reduce_vertices"],
               "| slowest root %.3f ms vertex %d (inlier rank %d)" % (c["slowest_root_ns"] / 1e6, c["slowest_root_vertex"], rank),
               "roots>1ms", c["roots_over_1ms"], "sum root ms %.1f" % (c["root_ns_total"] / 1e6),
-              "Mcycles first/reduce/colour %.1f %.1f %.1f" % (c["root_colour_cycles"] / 1e6, c["reduce_cycles"] / 1e6, c["colour_cycles"] / 1e6))
+              "Mcycles first/reduce/colour %.1f %.1f %.1f" % (c["root_colour_cycles"] / 1e6, c["reduce_cycles"] / 1e6, c["colour_cycles"] / 1e6),
+              "block-bound prunes", c["block_bound_prunes"], "flags", EXTRA)

@@ -35,7 +35,12 @@ namespace {
 constexpr int kHeurThreads = 512;
 constexpr int kPeelThreads = 1024;
 constexpr int kExactThreads = 256;
+#ifndef TZR_EXACT_MIN_BLOCKS
+#define TZR_EXACT_MIN_BLOCKS 3  // CTAs per SM the exact kernel is compiled for (80 registers; 2 -> 128)
+#endif
 constexpr int kExactWarps = kExactThreads / 32;
+constexpr int kBlkBatch = 16; // block colour bound: row words in flight per lane (x2, ping-pong)
+constexpr int kYU = 2;        // colouring: bitset words per lane whose row loads are issued together
 constexpr int kSpecCand = 8;  // colouring: candidates resolved per round trip to the bitset (see node_colour)
 
 __device__ __forceinline__ const uint32_t* adj_row32(const Batch& bt, int b, int v) {
@@ -712,6 +717,8 @@ struct WarpCtx {
   int b, n, W, lane;
   uint32_t *Pc, *Q, *R, *Bs;     // shared memory (this warp); words below xlo are never read nor written
   int* cand;                     // shared memory (this warp): kSpecCand candidate vertices of the colouring
+  int blk;                       // vertices per block of the block colour bound (0: W too small for it)
+  int bb_col, bb_vtx;            // colours / vertices of the blocks coloured so far in this problem (predicts the bound)
   uint32_t* stack;               // global: level d -> P at stack + d*2W, B at stack + d*2W + W
   int32_t* cv;                   // global: current clique
   int32_t* centry;               // global: clique size at entry of level d
@@ -736,7 +743,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     const int need = Lc - csz - 1;  // a candidate must have >= need neighbours inside P to reach size Lc
     for (int x = c.xlo + lane; x < W; x += 32) c.Q[x] = c.Pc[x];
     __syncwarp();
-    bool changed = false;
+    int removed = 0;
     int added = 0;
     {
       int x = c.xlo;
@@ -762,7 +769,7 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
             ++added;
           } else if (d[q] < need) {
             if (lane == 0) c.Q[u[q] >> 5] &= ~(1u << (u[q] & 31));
-            changed = true;
+            ++removed;
           }
         }
         if (kc < 4) break;
@@ -772,8 +779,10 @@ __device__ int node_reduce(WarpCtx& c, int& csz) {
     for (int x = c.xlo + lane; x < W; x += 32) c.Pc[x] = c.Q[x];
     __syncwarp();
     csz += added;
-    if (!changed) {
-      const int cnt2 = cnt - added;
+    // another round pays |P| row reads again: only when this one removed a good part of P (degrees drop by about as
+    // much, which is what makes further vertices fall)
+    if (removed * 8 < cnt) {
+      const int cnt2 = cnt - added - removed;
       const int Lc2 = *c.Lp + c.strict;
       if (csz + cnt2 < Lc2) return 0;
       if (cnt2 == 0) return 1;
@@ -823,15 +832,93 @@ __device__ int node_colour(WarpCtx& c, int csz) {
   }
   int nB = 0;
   int qstart = xlo;
-  for (int k = 1;; ++k) {
+  bool singles = false;  // the last class had one member: a clique-like remainder, try the singleton path first
+  int k = 1;
+  while (true) {
     // anything left uncoloured?
     int xq;
     const int first = warp_first_bit(c.Q, W, lane, qstart, &xq);
     if (first < 0) break;
     qstart = xq;
+    if (singles) {
+      // ---- singleton path.  When what is left is (nearly) a clique every vertex needs a class of its own, and the
+      // general loop would pay two round trips per class.  Here the rows of the lowest <= kSpecCand uncoloured
+      // vertices are read in ONE round trip (only the words where Q still has vertices) and each is tested for
+      // "no uncoloured non-neighbour above it"; the leading vertices that pass are the next classes, one each —
+      // exactly what the greedy rule yields, because a class started at u only looks at uncoloured vertices above u,
+      // and those are not changed by the singleton classes of lower vertices.
+      const int x = qstart + lane;
+      const uint32_t w = x < W ? c.Q[x] : 0u;
+      const int pc = __popc(w);
+      int incl = pc;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);  // >= 1: the first vertex lies in this window
+      {
+        int rank = incl - pc;
+        uint32_t ww = w;
+        while (ww && rank < kSpecCand) {
+          c.cand[rank++] = x * 32 + __ffs(ww) - 1;
+          ww &= ww - 1;
+        }
+      }
+      __syncwarp();
+      const int nc = total < kSpecCand ? total : kSpecCand;
+      int u[kSpecCand];
+      const uint32_t* r[kSpecCand];
+      uint32_t ne[kSpecCand];
+#pragma unroll
+      for (int q = 0; q < kSpecCand; ++q) {
+        u[q] = c.cand[q < nc ? q : 0];
+        r[q] = adj_row32(*c.bt, c.b, u[q]);
+        ne[q] = 0u;
+      }
+      for (int y = (u[0] >> 5) + lane; y < W; y += 32) {
+        const uint32_t qy = c.Q[y];
+        uint32_t rr[kSpecCand];
+#pragma unroll
+        for (int q = 0; q < kSpecCand; ++q) rr[q] = (qy != 0u && q < nc && y >= (u[q] >> 5)) ? r[q][y] : 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < kSpecCand; ++q) {
+          uint32_t tq = qy & ~rr[q];
+          if (y == (u[q] >> 5)) tq &= ~((2u << (u[q] & 31)) - 1u);  // strictly above u
+          ne[q] |= tq;
+        }
+      }
+      int ns = 0;  // leading singleton classes
+      bool open = true;
+#pragma unroll
+      for (int q = 0; q < kSpecCand; ++q) {
+        const bool nonempty = __any_sync(0xffffffffu, ne[q] != 0u);
+        if (q < nc && open && !nonempty) ++ns;
+        else open = false;
+      }
+      __syncwarp();
+      if (lane < ns) {
+        const int ul = c.cand[lane];
+        const uint32_t bit = 1u << (ul & 31);
+        atomicAnd(&c.Q[ul >> 5], ~bit);
+        if (k + lane >= kmin) {
+          atomicOr(&c.Bs[ul >> 5], bit);
+        }
+      }
+      for (int q = 0; q < ns; ++q)
+        if (k + q >= kmin) ++nB;
+      k += ns;
+      __syncwarp();
+      if (ns == nc) continue;       // all of them: look at the next ones the same way
+      if (ns == 0) singles = false; // not clique-like (any more)
+      const int first2 = warp_first_bit(c.Q, W, lane, qstart, &xq);
+      if (first2 < 0) break;
+      qstart = xq;
+    }
+    // ---- general path: one class, the greedy maximal independent set of Q
     for (int x = qstart + lane; x < W; x += 32) c.R[x] = c.Q[x];
     __syncwarp();
     int xr = qstart;
+    int members = 0;
     while (xr < W) {
       // ---- the lowest <= kSpecCand vertices of R inside the 32-word window at xr
       const int x = xr + lane;
@@ -874,17 +961,39 @@ __device__ int node_colour(WarpCtx& c, int csz) {
         const unsigned col = (em >> (j * (j - 1) / 2)) & ((1u << j) - 1u);  // bit i: candidate i adjacent to j
         if (j < nc && !(col & acc)) acc |= 1u << j;
       }
-      // ---- (2) R &= ~(union of the accepted rows), each row from its own word upwards
+      // ---- (2) R &= ~(union of the accepted rows), each row from its own word upwards, only where R has vertices
       const uint32_t* r[kSpecCand];
 #pragma unroll
       for (int q = 0; q < kSpecCand; ++q) r[q] = adj_row32(*c.bt, c.b, u[q]);
-      for (int y = (u[0] >> 5) + lane; y < W; y += 32) {
-        uint32_t m = 0u;
+      int left = 0;
+      // groups of kYU words per lane: all row loads of a group are issued before any is used (no branch in between:
+      // a data-dependent branch around the loads costs one round trip per word instead of one per group)
+      for (int y0 = (u[0] >> 5) + lane; y0 < W; y0 += 32 * kYU) {
+        uint32_t rw[kYU], m[kYU];
 #pragma unroll
-        for (int q = 0; q < kSpecCand; ++q)
-          if (((acc >> q) & 1u) && y >= (u[q] >> 5)) m |= r[q][y];
-        c.R[y] &= ~m;
+        for (int t = 0; t < kYU; ++t) {
+          const int y = y0 + 32 * t;
+          rw[t] = y < W ? c.R[y] : 0u;
+          m[t] = 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < kYU; ++t) {
+          const int y = y0 + 32 * t;
+#pragma unroll
+          for (int q = 0; q < kSpecCand; ++q)
+            if (rw[t] != 0u && ((acc >> q) & 1u) && y >= (u[q] >> 5)) m[t] |= r[q][y];
+        }
+#pragma unroll
+        for (int t = 0; t < kYU; ++t) {
+          const int y = y0 + 32 * t;
+          if (rw[t] != 0u) {
+            const uint32_t nw = rw[t] & ~m[t];
+            c.R[y] = nw;
+            left += __popc(nw);
+          }
+        }
       }
+      left = __reduce_add_sync(0xffffffffu, left);  // includes the accepted candidates themselves
       __syncwarp();
       if (lane < nc && ((acc >> lane) & 1u)) {
         const int ul = c.cand[lane];
@@ -893,12 +1002,181 @@ __device__ int node_colour(WarpCtx& c, int csz) {
         atomicAnd(&c.Q[ul >> 5], ~bit);
         if (k >= kmin) atomicOr(&c.Bs[ul >> 5], bit);
       }
-      if (k >= kmin) nB += __popc(acc);
+      const int na = __popc(acc);
+      members += na;
+      if (k >= kmin) nB += na;
       xr = xlast;  // everything below the last candidate is decided
       __syncwarp();
+      if (left == na) break;  // nothing but the picks themselves was left: the class is complete
     }
+    singles = members == 1 && !(c.bt->flags_dbg & 8192u);  // 8192: A/B switch
+    ++k;
   }
   return nB;
+}
+
+// Block colour bound of the node in Pc: true when it proves that the node cannot even tie the incumbent.
+//
+// The full greedy colouring reads one adjacency row per vertex of P, a few per dependent round trip.  Most roots need
+// far less: an outlier's later neighbourhood is a sparse random graph whose clique number is an order of magnitude
+// below the incumbent.  Here P is cut (in index order) into blocks of <= blk vertices that lie within 32 consecutive
+// bitset words; for a block, ONE word of every member's row covers the whole block, so the induced blk x blk
+// adjacency is fetched with independent loads (one round trip), packed to local numbering in shared memory (the Q/R/Bs
+// scratch, unused at this point) and coloured greedily without touching global memory again.  Colours of different
+// blocks are different colours, so the sum over the blocks is a valid (weaker) colour bound: ~0.085 colours per vertex
+// at 15 % density and 128-vertex blocks against ~0.04 for the full greedy colouring — enough whenever
+// |P| is below ~12x the incumbent size, at a fraction of the row traffic and without the dependent round trips.
+__device__ bool node_block_bound(WarpCtx& c, int csz) {
+  const int W = c.W, lane = c.lane, S = c.blk;
+  const int kmin = *c.Lp + c.strict - csz;
+  if (S == 0 || kmin <= 1 || (c.bt->flags_dbg & 4096u)) return false;  // 4096: A/B switch (bench/profiling)
+  const int SW = S >> 5;                  // words per local row
+  uint32_t* M = c.Q;                      // S x SW local adjacency (Q, R, Bs are contiguous: 3 W words)
+  int* list = reinterpret_cast<int*>(M + S * SW);  // S global vertex ids
+  int remaining = warp_popc(c.Pc, W, lane, c.xlo);
+  // colours per vertex seen so far in this problem say the bound would come out above kmin: do not pay for it
+  if (c.bb_vtx >= 4 * S && (long long)remaining * c.bb_col > (long long)(kmin + (kmin >> 3)) * c.bb_vtx) return false;
+  int colours = 0;
+  int x = c.xlo;
+  uint32_t carry = 0xffffffffu;  // bits of word x not yet consumed by an earlier block
+  while (x < W && remaining > 0) {
+    if (colours + remaining < kmin) return true;
+    // ---- the block: the next <= S vertices of P inside words [x, x + 32)
+    const int xw = x + lane;
+    uint32_t w = xw < W ? c.Pc[xw] : 0u;
+    if (lane == 0) w &= carry;
+    int pc = __popc(w);
+    int incl = pc;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) {
+      x += 32;
+      carry = 0xffffffffu;
+      continue;
+    }
+    int off = incl - pc;  // local number of this lane's first vertex
+    int xnext = x + 32;
+    uint32_t cnext = 0xffffffffu;
+    if (total > S) {
+      // cut after the S-th vertex: the lane holding it keeps its lowest (S - off) bits, later lanes nothing
+      uint32_t keep = w;
+      if (off >= S) keep = 0u;
+      else if (incl > S) {
+        uint32_t m = w;
+        keep = 0u;
+        for (int q = 0; q < S - off; ++q) {
+          keep |= m & (0u - m);
+          m &= m - 1;
+        }
+      }
+      const unsigned cutl = __ballot_sync(0xffffffffu, incl > S && off < S) | __ballot_sync(0xffffffffu, off >= S && pc > 0);
+      const int ln = __ffs(cutl) - 1;  // first lane with unconsumed vertices
+      const uint32_t wn = __shfl_sync(0xffffffffu, w & ~keep, ln);
+      xnext = x + ln;
+      cnext = wn;  // word xnext keeps exactly its unconsumed bits (the original word ANDed again next time)
+      w = keep;
+      pc = __popc(w);
+    }
+    const int nb = total > S ? S : total;
+    remaining -= nb;
+    // ---- vertex list and zeroed local matrix
+    {
+      uint32_t m = w;
+      int q = off;
+      while (m) {
+        list[q++] = xw * 32 + __ffs(m) - 1;
+        m &= m - 1;
+      }
+    }
+    for (int q = lane; q < nb * SW; q += 32) M[q] = 0u;
+    __syncwarp();
+    // ---- rows: word xw of every member's row, packed to local numbering (software bit-gather on the lane's mask w).
+    // Two batches of kBlkBatch independent loads are kept in flight (ping-pong) while the previous batch is packed.
+    if (pc > 0) {
+      const int wo = off >> 5, sh = off & 31;
+      const uint32_t* colp = reinterpret_cast<const uint32_t*>(c.bt->adj) + (size_t)c.b * c.n * W + xw;  // word xw of row 0
+      auto load = [&](uint32_t (&dst)[kBlkBatch], int i0) {
+#pragma unroll
+        for (int q = 0; q < kBlkBatch; ++q) {
+          const int i = i0 + q < nb ? i0 + q : nb - 1;
+          dst[q] = colp[(size_t)list[i] * W];
+        }
+      };
+      auto pack = [&](const uint32_t (&src)[kBlkBatch], int i0) {
+#pragma unroll
+        for (int q = 0; q < kBlkBatch; ++q) {
+          if (i0 + q < nb) {
+            const uint32_t a = src[q] & w;
+            if (a) {
+              uint32_t val = 0u, m = w;
+              int kbit = 0;
+              while (m) {
+                const int bpos = __ffs(m) - 1;
+                m &= m - 1;
+                val |= ((a >> bpos) & 1u) << kbit;
+                ++kbit;
+              }
+              uint32_t* row = M + (i0 + q) * SW;
+              atomicOr(row + wo, val << sh);
+              if (sh && (val >> (32 - sh))) atomicOr(row + wo + 1, val >> (32 - sh));
+            }
+          }
+        }
+      };
+      uint32_t ra[kBlkBatch], rb[kBlkBatch];
+      load(ra, 0);
+      for (int i0 = 0; i0 < nb; i0 += 2 * kBlkBatch) {
+        if (i0 + kBlkBatch < nb) load(rb, i0 + kBlkBatch);
+        pack(ra, i0);
+        if (i0 + 2 * kBlkBatch < nb) load(ra, i0 + 2 * kBlkBatch);
+        if (i0 + kBlkBatch < nb) pack(rb, i0 + kBlkBatch);
+      }
+    }
+    __syncwarp();
+    // ---- greedy colouring of the block in shared memory (warp-uniform scalar work on <= 4-word sets)
+    {
+      uint32_t U[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lo = j * 32;
+        if (lo < nb) U[j] = nb - lo >= 32 ? 0xffffffffu : ((1u << (nb - lo)) - 1u);
+      }
+      c.bb_vtx += nb;
+      while ((U[0] | U[1] | U[2] | U[3]) != 0u) {
+        ++colours;
+        ++c.bb_col;
+        uint32_t R[4] = {U[0], U[1], U[2], U[3]};
+        while (true) {
+          int u = -1;
+#pragma unroll
+          for (int j = 3; j >= 0; --j)
+            if (R[j]) u = j * 32 + __ffs(R[j]) - 1;
+          if (u < 0) break;
+          const uint32_t* row = M + u * SW;
+          const uint32_t bit = 1u << (u & 31);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < SW) {
+              uint32_t rj = row[j];
+              if (j == (u >> 5)) {
+                rj |= bit;
+                U[j] &= ~bit;
+              }
+              R[j] &= ~rj;
+            }
+          }
+        }
+        if (colours >= kmin) return false;  // this bound cannot decide: the caller colours P properly
+      }
+    }
+    __syncwarp();
+    x = xnext;
+    carry = cnext;
+  }
+  return colours < kmin;
 }
 
 // Offer the clique cv[0..csz) as incumbent.  Larger wins; on equal size the lexicographically smaller
@@ -958,6 +1236,8 @@ __device__ void record_clique(WarpCtx& c, int csz) {
 __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
   const int n = bt.n, W = c.W, lane = c.lane;
   c.b = b;
+  c.bb_col = 0;
+  c.bb_vtx = 0;
   c.Lp = bt.L + b;
   c.strict = (bt.flags[b] & 8) ? 1 : 0;
   const int ub_stop = c.strict ? (bt.flags[b] >> 8) : 0x7fffffff;  // LP bound of the NT step: reaching it ends the search
@@ -1023,7 +1303,10 @@ __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
           // the incumbent): try it before paying the same number of row reads for the degree rules.
           const int cnt = warp_popc(c.Pc, W, lane, c.xlo);
           if (csz + cnt < *c.Lp + c.strict) r = 0;
-          else if (cnt > 0 && node_colour(c, csz) == 0) r = 0;
+          else if (cnt > 0 && node_block_bound(c, csz)) {
+            r = 0;
+            if (c.cnt && lane == 0) atomicAdd(c.cnt + 14, 1ull);
+          } else if (cnt > 0 && node_colour(c, csz) == 0) r = 0;
           at_root = false;
           if (c.cnt) {
             const long long ck1 = clock64();
@@ -1107,7 +1390,7 @@ __device__ void exact_search_problem(const Batch& bt, WarpCtx& c, int b) {
 // move on together: at most ~exact_conc adjacency bitsets are live at a time, chosen on the host so that they fit the
 // L2 (one 10k-vertex bitset is 12.5 MB; a chunk of eight of them under search at once ran at HBM speed, ~2.7x slower
 // per problem than one at a time).  Scratch (stack, clique, entry sizes) belongs to the warp, not to the problem.
-__global__ void __launch_bounds__(kExactThreads, 3) clique_exact_kernel(Batch bt) {
+__global__ void __launch_bounds__(kExactThreads, TZR_EXACT_MIN_BLOCKS) clique_exact_kernel(Batch bt) {
   const int n = bt.n, W = pitch32(n), B = bt.B;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1124,6 +1407,11 @@ __global__ void __launch_bounds__(kExactThreads, 3) clique_exact_kernel(Batch bt
   c.R = wbase + 2 * W;
   c.Bs = wbase + 3 * W;
   c.cand = reinterpret_cast<int*>(wbase + 4 * W);
+  {
+    int S = 128;  // block colour bound: S*S/32 matrix words + S list entries must fit the 3 W scratch words
+    while (S > 0 && S * (S >> 5) + S > 3 * W) S -= 32;
+    c.blk = S;
+  }
   const size_t gw = (size_t)blockIdx.x * kExactWarps + wid;  // this warp's scratch slot
   c.stack = bt.stack + gw * (size_t)bt.max_depth * 2 * W;
   c.cv = bt.cv + gw * (size_t)n;
