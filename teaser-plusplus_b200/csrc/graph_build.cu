@@ -143,9 +143,16 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
       gc.pad2 = 0;
     }
     // ---- tensor-core filter constants (graph_tc.cu; derivation in DESIGN.md §3.1).  a' = |ds|^2 and b' = |dd|^2 come
-    // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb (E = ea + eb); the kernel forms t' = a'-b' and
-    // d' = t'^2 - beta^2 (sqrt a' + sqrt b')^2 in FP32 and decides by the sign of d' unless
-    //   d'^2 <= t'^2 (k1 + k2 t'^2)   [ >= ( 16 E |t'| + 24 u t'^2 )^2 : the band ]   or  a' <= ga  or  b' <= gb.
+    // out of the tensor core with |a' - a| <= ea, |b' - b| <= eb (E = ea + eb).  With t = a - b, s = a + b,
+    //   f(a, b) = t^2 - 2 beta^2 s + beta^4 = (g^2 - beta^2)(w - beta^2),  g = |sqrt a - sqrt b|,  w = (sqrt a + sqrt b)^2 >= s
+    // so   edge  <=>  s <= beta^2  or  f <= 0   — a polynomial, no square root, no division:
+    //   |f(a', b') - f(a, b)| <= 2 E |t'| + E^2 + 2 beta^2 E                      (tensor-core error)
+    //   |d^ - f(a', b')|      <= 8 u (t'^2 + 2 beta^2 s' + beta^4)                 (FP32 evaluation of d^: 4 roundings + 2 constants)
+    // and for s <= beta^2 (where the sign of f says nothing)  f <= (beta^2 - s)^2 <= beta^4.  The kernel decides by the
+    // signs of d^ +- band, band = kap (t'^2 + beta^4) + c0 with 2 E |t'| <= (E/lam) t'^2 + E lam (lam = the typical |t| at the
+    // threshold, 0.75 beta D): kap = E/lam + 8 u, c0 = E lam + E^2 + 2 beta^2 E + 16 u beta^2 Smax + 8 u beta^4 + beta^4.
+    // (8 u t'^2 needs no case split: it is part of kap.)  d^ + band < 0 proves f < 0 (an edge whatever s is); d^ - band >= 0
+    // proves f > beta^4, hence s > beta^2 and a non-edge; everything else goes to the exact FP64 re-check.
     {
       double Ds2 = 0, Dd2 = 0;  // largest possible squared distance inside each (scaled) cloud
       for (int k = 0; k < 3; ++k) {
@@ -155,19 +162,23 @@ __global__ void __launch_bounds__(256) prep_kernel(Batch bt) {
       }
       const double kappa = bt.tc_kappa > 0 ? bt.tc_kappa : kTcKappa;
       const double ea = kappa * u32 * Ds2, eb = kappa * u32 * Dd2, E = ea + eb;
-      // guards: sqrt(a') >= max(16 ea / beta, beta / 4) (same for b'): the first keeps |g' - g| <= beta/8, the second
-      // bounds the sqrt(b'/a') sensitivity of w near the threshold by 4.5; band constant 2.43 * (2 + 4.5) = 15.8
-      const double ra = fmax(16.0 * ea / beta, 0.25 * beta), rb = fmax(16.0 * eb / beta, 0.25 * beta);
-      const double ga = ra * ra, gb = rb * rb;
-      const double ct = 16.0 * E, cf = 24.0 * u32;
+      const double b2 = beta * beta, b4 = b2 * b2;
+      const double lam = 0.75 * beta * sqrt(0.5 * (Ds2 + Dd2));
+      const double Smax = Ds2 + Dd2 + E;
+      const double kap = E / lam + 8.0 * u32;
+      const double c0 = E * lam + E * E + 2.0 * b2 * E + 16.0 * u32 * b2 * Smax + 8.0 * u32 * b4 + b4;
+      // When is the filter worth it (correctness never depends on this)?  beta <= D/8: the beta^4 floor of the band stays
+      // below ~1e-3 of the pairs (measured 3.5e-5 at C2's beta/D = 1/26, 7.8e-4 at 1/4); E / (0.75 D) <= beta / 64: the band in g = |sqrt a - sqrt b| is a small fraction of the
+      // threshold (fails when the noise bound is tiny against the extent of a cloud: beta/D below ~3e-4); b4 a normal float.
+      const double Dmin = sqrt(fmin(Ds2, Dd2));
       const bool ok = !use64 && (bt.flags_dbg & 1024u) != 0 && (bt.flags_dbg & 512u) == 0 && Ds2 > 0 && Dd2 > 0 && Ds2 < 1e8 && Dd2 < 1e8 &&
-                      beta * beta > 1e-30 && isfinite(E) && ga <= Ds2 / 256.0 && gb <= Dd2 / 256.0;
+                      b4 > 1e-30 && isfinite(E) && isfinite(kap) && 8.0 * beta <= Dmin && 64.0 * E <= 0.75 * Dmin * beta;
       gc.use_tc = ok ? 1 : 0;
-      gc.tc_beta2 = (float)(beta * beta);
-      gc.tc_k1 = (float)(2.0 * ct * ct * up);
-      gc.tc_k2 = (float)(2.0 * cf * cf * up);
-      gc.tc_ga = fmaxf((float)(ga * up), 1e-36f);
-      gc.tc_gb = fmaxf((float)(gb * up), 1e-36f);
+      gc.tc_c2 = (float)(2.0 * b2);
+      gc.tc_b4 = (float)b4;
+      gc.tc_kap = (float)(kap * up);
+      gc.tc_c0 = (float)(c0 * up);
+      gc.tc_pad = 0.f;
       if (ok && bt.rechecks) atomicAdd(bt.mismatches + 7, 1ull);  // debug counter 7: problems on the tensor-core path
     }
     bt.gc[b] = gc;

@@ -209,75 +209,31 @@ __device__ __forceinline__ float sqrt_approx_tc(float x) {  // MUFU.SQRT, max re
 }
 
 struct TcConsts {
-  f32x2 two, nbeta2, nk1, nk2;
-  float ga, gb;
+  f32x2 nc2, b4, kap, c0;  // -2 beta^2, beta^4, band slope, band offset (prep_kernel)
 };
 
-// d = t^2 - beta^2 (sqrt a + sqrt b)^2 and the band test value r = d^2 - t^2 (k1 + k2 t^2) for two pairs; shared by
-// the sweep and the (rare) revisit so both see identical values.  nk1 / nk2 hold -k1 / -k2.
-__device__ __forceinline__ void tc_pair2(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, const TcConsts& k,
-                                         float& d0, float& d1, float& r0, float& r1) {
-  const f32x2 A = pk2(a0, a1), B = pk2(b0, b1);
-  const f32x2 t = sub2(A, B), s = add2(A, B), p = mul2(A, B);
-  float p0, p1;
-  upk2(p, p0, p1);
-  const f32x2 q = pk2f(sqrt_approx_tc(p0), sqrt_approx_tc(p1));
-  const f32x2 w = fma2(q, k.two, s), t2 = mul2(t, t), d = fma2(w, k.nbeta2, t2);
-  const f32x2 nz = fma2(t2, k.nk2, k.nk1), ny = mul2(t2, nz), r = fma2(d, d, ny);
-  upk2(d, d0, d1);
-  upk2(r, r0, r1);
-}
-
-// 16 pairs (columns c0 .. c0+15 of the warp's 32): shifts their sign bits into `word` (call with the upper half first)
-// and folds the band / guard minima.  Two phases so that the eight MUFU pairs are in flight together: with the
-// consumer right behind each MUFU.SQRT a warp stalls for the XU latency once per pair group (measured: ~50 clk per
-// pair step per warp, latency-bound at 16 warps per SM).
-__device__ __forceinline__ void tc_sweep16(uint32_t ta, uint32_t tb, const TcConsts& k, uint32_t& word, float& m1,
-                                           float& ma, float& mb) {
-  uint32_t ra[16], rb[16];
-  tmem_ld16(ta, ra);
-  tmem_ld16(tb, rb);
-  tmem_wait_ld();
-  f32x2 T[8], Sm[8], Q[8];
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const f32x2 A = pk2(ra[2 * g], ra[2 * g + 1]), B = pk2(rb[2 * g], rb[2 * g + 1]);
-    T[g] = sub2(A, B);
-    Sm[g] = add2(A, B);
-    float p0, p1;
-    upk2(mul2(A, B), p0, p1);
-    Q[g] = pk2f(sqrt_approx_tc(p0), sqrt_approx_tc(p1));
-    ma = fminf(ma, fminf(__uint_as_float(ra[2 * g]), __uint_as_float(ra[2 * g + 1])));
-    mb = fminf(mb, fminf(__uint_as_float(rb[2 * g]), __uint_as_float(rb[2 * g + 1])));
-  }
+// 16 pairs (columns c0 .. c0+15 of the warp's 32; call with the upper half first).  Per pair, packed two at a time:
+//   t = a - b, s = a + b, P = t^2 + beta^4, d = P - 2 beta^2 s  [= (g^2 - beta^2)(w - beta^2)],  band = kap P + c0,
+//   d_hi = d + band  (sign bit 1: surely an edge),   d_lo = d - band  (sign bit 0: surely not an edge)
+// = 7 FP32 lane operations, no MUFU, no compare; the two sign bits are funnel-shifted into the words.
+__device__ __forceinline__ void tc_sweep16(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const TcConsts& k,
+                                           uint32_t& whi, uint32_t& wlo) {
 #pragma unroll
   for (int g = 7; g >= 0; --g) {
-    const f32x2 w = fma2(Q[g], k.two, Sm[g]), t2 = mul2(T[g], T[g]), d = fma2(w, k.nbeta2, t2);
-    const f32x2 nz = fma2(t2, k.nk2, k.nk1), ny = mul2(t2, nz), r = fma2(d, d, ny);
-    float d0, d1, r0, r1;
-    upk2(d, d0, d1);
-    upk2(r, r0, r1);
-    word = __funnelshift_l(__float_as_uint(d1), word, 1);
-    word = __funnelshift_l(__float_as_uint(d0), word, 1);
-    m1 = fminf(m1, fminf(r0, r1));
+    const f32x2 A = pk2(ra[2 * g], ra[2 * g + 1]), B = pk2(rb[2 * g], rb[2 * g + 1]);
+    const f32x2 t = sub2(A, B), s = add2(A, B);
+    const f32x2 P = fma2(t, t, k.b4);
+    const f32x2 d = fma2(s, k.nc2, P);
+    const f32x2 bd = fma2(P, k.kap, k.c0);
+    const f32x2 dh = add2(d, bd), dl = sub2(d, bd);
+    float h0, h1, l0, l1;
+    upk2(dh, h0, h1);
+    upk2(dl, l0, l1);
+    whi = __funnelshift_l(__float_as_uint(h1), whi, 1);
+    whi = __funnelshift_l(__float_as_uint(h0), whi, 1);
+    wlo = __funnelshift_l(__float_as_uint(l1), wlo, 1);
+    wlo = __funnelshift_l(__float_as_uint(l0), wlo, 1);
   }
-}
-
-// the same 16 pairs again: which of them are undecided
-__device__ __forceinline__ uint32_t tc_flags16(uint32_t ta, uint32_t tb, const TcConsts& k) {
-  uint32_t ra[16], rb[16];
-  tmem_ld16(ta, ra);
-  tmem_ld16(tb, rb);
-  tmem_wait_ld();
-  uint32_t f = 0u;
-#pragma unroll
-  for (int c = 0; c < 16; c += 2) {
-    float d0, d1, r0, r1;
-    tc_pair2(ra[c], ra[c + 1], rb[c], rb[c + 1], k, d0, d1, r0, r1);
-    if (!(r0 > 0.f) || !(__uint_as_float(ra[c]) > k.ga) || !(__uint_as_float(rb[c]) > k.gb)) f |= 1u << c;
-    if (!(r1 > 0.f) || !(__uint_as_float(ra[c + 1]) > k.ga) || !(__uint_as_float(rb[c + 1]) > k.gb)) f |= 2u << c;
-  }
-  return f;
 }
 
 // 32x32 bit transpose across the lanes of a warp (lane l passes row l, receives column l)
@@ -419,50 +375,71 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
     int rdeg = 0;
     const int P32 = pitch32(n);
     TcConsts kc;
-    kc.two = pk2f(2.f, 2.f);
-    kc.nbeta2 = kc.nk1 = kc.nk2 = kc.two;
-    kc.ga = kc.gb = 0.f;
+    kc.nc2 = kc.b4 = kc.kap = kc.c0 = pk2f(0.f, 0.f);
     const GraphConsts* gcp = bt.gc;
     bool use_tc = false;
+    uint32_t* adj32 = nullptr;  // bitset of the strip's problem
+    uint32_t* rowp = nullptr;   // row i of it
+    int* degp = nullptr;
+    int i = 0;
+    bool row_ok = false, row_edge = false;
     while (ti.next()) {
       if (ti.first) {  // per strip, not per tile: the load sits on the critical path of the tile hand-off
         gcp = bt.gc + ti.b;
         use_tc = gcp->use_tc != 0;
       }
       if (!use_tc) continue;
-      const int b = ti.b, I = ti.I, J = ti.J;
+      const int I = ti.I, J = ti.J;
       if (ti.first) {
-        kc.nbeta2 = pk2f(-gcp->tc_beta2, -gcp->tc_beta2);
-        kc.nk1 = pk2f(-gcp->tc_k1, -gcp->tc_k1);
-        kc.nk2 = pk2f(-gcp->tc_k2, -gcp->tc_k2);
-        kc.ga = gcp->tc_ga;
-        kc.gb = gcp->tc_gb;
+        kc.nc2 = pk2f(-gcp->tc_c2, -gcp->tc_c2);
+        kc.b4 = pk2f(gcp->tc_b4, gcp->tc_b4);
+        kc.kap = pk2f(gcp->tc_kap, gcp->tc_kap);
+        kc.c0 = pk2f(gcp->tc_c0, gcp->tc_c0);
+        i = I * kTile + 32 * q + lane;
+        adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)ti.b * n * P32;
+        rowp = adj32 + (size_t)i * P32;
+        degp = bt.deg + (size_t)ti.b * n;
+        row_ok = i < n;
+        row_edge = I * kTile + kTile > n;  // some rows of the block lie past n
       }
-      const int i = I * kTile + 32 * q + lane;
       const int j0 = J * kTcN + 32 * h;
-      uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)b * n * P32;
-      int* degp = bt.deg + (size_t)b * n;
       const uint32_t ts = n_t & 1u;
       mbar_wait(bar(kBarTFull + ts), (n_t >> 1) & 1u);
       fence_after_sync();
       const uint32_t ta = tbase + lane_base + 128u * ts + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
-      // ---- sweep: bit k of word = sign(d_k), i.e. pair (i, j0+k) classified as an edge
-      uint32_t word = 0u;
-      float m1 = __int_as_float(0x7f800000), ma = m1, mb = m1;
-      tc_sweep16(ta + 16u, tb + 16u, kc, word, m1, ma, mb);
-      tc_sweep16(ta, tb, kc, word, m1, ma, mb);
-      // validity of the pairs of this thread: columns < n, row < n, i != j
-      uint32_t vmask = j0 + 32 <= n ? 0xffffffffu : (j0 >= n ? 0u : ((1u << (n - j0)) - 1u));
-      if (i >= n) vmask = 0u;
-      if (i >= j0 && i < j0 + 32) vmask &= ~(1u << (i - j0));
-      const bool flagged = !(m1 > 0.f) || !(ma > kc.ga) || !(mb > kc.gb);
-      if (kVerify || __any_sync(0xffffffffu, flagged && vmask != 0u)) {
-        // ---- rare: find the undecided pairs of this thread.  They keep their tentative bit (sign of d) and are queued
-        // for tc_patch_kernel, which evaluates the reference's exact FP64 sequence and flips the bits that disagree —
-        // so no warp of this kernel waits for double-precision square roots while seven others wait for its
-        // accumulator stage.  (Queue full: evaluated here.)
-        uint32_t fmask = tc_flags16(ta, tb, kc) | (tc_flags16(ta + 16u, tb + 16u, kc) << 16);
-        fmask &= vmask;
+      // ---- sweep: whi bit k = pair (i, j0+k) surely an edge, wlo bit k = not surely a non-edge.  The second half of the
+      // accumulators is in flight while the first is evaluated; the stage goes back to the MMA issuer as soon as the
+      // warp's 2 x 32 x 32 values sit in registers.
+      uint32_t whi = 0u, wlo = 0u;
+      {
+        uint32_t a1[16], b1[16], a0[16], b0[16];
+        tmem_ld16(ta + 16u, a1);
+        tmem_ld16(tb + 16u, b1);
+        tmem_wait_ld();
+        tmem_ld16(ta, a0);
+        tmem_ld16(tb, b0);
+        tc_sweep16(a1, b1, kc, whi, wlo);
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kBarTEmpty + ts));
+        tc_sweep16(a0, b0, kc, whi, wlo);
+      }
+      // validity of the pairs of this thread: columns < n, row < n, i != j (interior tiles: everything valid)
+      uint32_t vmask = 0xffffffffu;
+      const bool diag = (J >> 1) == I;
+      if (row_edge || diag || j0 + 32 > n) {
+        vmask = j0 + 32 <= n ? 0xffffffffu : (j0 >= n ? 0u : ((1u << (n - j0)) - 1u));
+        if (!row_ok) vmask = 0u;
+        if (i >= j0 && i < j0 + 32) vmask &= ~(1u << (i - j0));
+      }
+      uint32_t word = whi & vmask;             // tentative classification: undecided pairs keep bit 0
+      uint32_t fmask = wlo & ~whi & vmask;     // undecided: inside the error band of the tensor-core norms
+      if (kVerify || __any_sync(0xffffffffu, fmask != 0u)) {
+        // ---- the undecided pairs are queued for tc_patch_kernel, which evaluates the reference's exact FP64 sequence
+        // and sets the bits of the edges among them — so no warp of this kernel waits for double-precision square roots.
+        // (Queue full: evaluated here.)
+        const int b = ti.b;
         const double* src = bt.src + (size_t)b * n * 3;
         const double* dst = bt.dst + (size_t)b * n * 3;
         const double beta = gcp->beta;
@@ -500,13 +477,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
             }
           } else {  // queue full (the count keeps growing; the patch kernel clamps it): exact evaluation in place
             // the first warp that does not fit leaves [base, cap) unwritten: void entries (b = ~0) for the patch kernel
-            for (unsigned int q = base + (unsigned int)lane; q < bt.tc_list_cap; q += 32u) bt.tc_list[q] = make_uint2(0xffffffffu, 0u);
+            for (unsigned int e = base + (unsigned int)lane; e < bt.tc_list_cap; e += 32u) bt.tc_list[e] = make_uint2(0xffffffffu, 0u);
             int nre = 0;
             while (fmask) {
               const int k = __ffs(fmask) - 1;
               fmask &= fmask - 1;
               const bool ex = scale_mode ? edge_exact_scale(src, dst, i, j0 + k, beta, s_hat) : edge_exact(src, dst, i, j0 + k, beta);
-              word = (word & ~(1u << k)) | ((ex ? 1u : 0u) << k);
+              word |= (ex ? 1u : 0u) << k;
               ++nre;
             }
             if (bt.rechecks) {
@@ -516,14 +493,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
           }
         }
       }
-      // hand the accumulator stage back to the MMA issuer (all TMEM reads of this warp are complete)
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarTEmpty + ts));
-      word &= vmask;
       rdeg += __popc(word);
-      if (i < n) adj32[(size_t)i * P32 + 2 * J + h] = word;
-      if ((J >> 1) != I) {  // transposed half: lane l holds column j0+l over rows I*128 + 32q .. +31
+      if (row_ok) rowp[2 * J + h] = word;
+      if (!diag) {  // transposed half: lane l holds column j0+l over rows I*128 + 32q .. +31
         const uint32_t colw = tc_transpose32(word, lane);
         const int jc = j0 + lane;
         if (jc < n) {
@@ -532,7 +504,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
         }
       }
       if (ti.last_of_strip()) {
-        if (i < n && rdeg) atomicAdd(degp + i, rdeg);
+        if (row_ok && rdeg) atomicAdd(degp + i, rdeg);
         rdeg = 0;
       }
       ++n_t;

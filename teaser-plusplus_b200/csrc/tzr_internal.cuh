@@ -42,11 +42,12 @@ struct GraphConsts {
   float f3_eps;          // bias of the squared norms (keeps w > 0)
   int pad2;
   double s_hat;   // scale applied to the centred source copies (1 unless estimate_scaling)
-  // tensor-core filter (graph_tc.cu): d = (a-b)^2 - beta^2 (sqrt(a)+sqrt(b))^2 from the Gram-form squared norms
+  // tensor-core filter (graph_tc.cu): d = (a-b)^2 - 2 beta^2 (a+b) + beta^4 from the Gram-form squared norms (no square root)
   int use_tc;     // 1: this problem goes through graph_tc_kernel, 0: through the CUDA-core strip kernel
-  float tc_beta2; // beta^2
-  float tc_k1, tc_k2;  // d^2 <= t^2 (k1 + k2 t^2) : undecided -> exact FP64 re-check   (t = a - b)
-  float tc_ga, tc_gb;  // a < ga or b < gb         : undecided -> exact FP64 re-check (tiny / cancelled squared norms)
+  float tc_c2;    // 2 beta^2
+  float tc_b4;    // beta^4
+  float tc_kap, tc_c0;  // |d| <= kap (t^2 + beta^4) + c0 : undecided -> exact FP64 re-check   (t = a - b)
+  float tc_pad;
 };
 
 // Everything the device kernels need to know about one batch (passed by value).
