@@ -20,3 +20,6 @@ ncu -i gpurun_out/r02_graph_tc3.ncu-rep --page raw --csv > gpurun_out/r02_graph_
 ncu -i gpurun_out/r02_graph_tc3.ncu-rep --page details --csv > gpurun_out/r02_graph_tc3_b128_ncu_details.csv 2>/dev/null
 ncu -i gpurun_out/r02_graph_tc3.ncu-rep --page source --csv > gpurun_out/r02_graph_tc3_b128_ncu_source.csv 2>/dev/null
 ls -la gpurun_out | tail -12
+# --- illegal memory access of HEAD's exact clique kernel at full-size C3: locate it
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python scripts/solve_one.py C3 0 1 > gpurun_out/r02_memcheck_C3.log 2>&1; echo "memcheck C3 rc=$?"
+grep -m 40 -E "Invalid|at |by thread|Address|ERROR SUMMARY|clique" gpurun_out/r02_memcheck_C3.log | head -60

@@ -14,7 +14,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
 rep = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 pr = synth.config_problem(cfg, 0, n=n)
 ctx = capi.Context(0)
-ctx.set_flags(4)
+ctx.set_flags(4 | int(os.environ.get('PROBE_FLAGS', '0')))
 p = capi.default_params(noise_bound=pr["noise_bound"], estimate_scaling=0, rotation_cost_threshold=1e-12)
 for _ in range(rep):
     g = ctx.solve(pr["src"], pr["dst"], p)

@@ -35,14 +35,17 @@ namespace tzr {
 using namespace tc;
 
 constexpr int kTcEpiWarps = 8;                        // warp w: TMEM lanes 32*(w&3).., columns 32*(w>>2)..
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);    // + 1 producer warp (TMA + MMA issue by one elected lane)
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 2);    // + warp 8: one lane drives the TMA engine, + warp 9: one lane issues the MMAs
+constexpr int kTcCtasPerSm = 3;                       // 24 epilogue warps per SM: the epilogue is latency-bound per warp
 constexpr int kTcN = 64;                              // columns of one tile (MMA N)
 constexpr int kTcPlaneA = 128 * 16;                   // A role: 128 rows x 4 tf32 per plane
 constexpr int kTcPlaneB = kTcN * 16;                  // B role: 64 rows x 4 tf32 per plane
 constexpr int kTcCloudA = 6 * kTcPlaneA, kTcCloudB = 6 * kTcPlaneB;   // 6 planes = K 24
 constexpr int kTcTileA = 2 * kTcCloudA;               // src + dst: 24 KB per 128-row block
 constexpr int kTcTileB = 2 * kTcCloudB;               // 12 KB per 64-column block
-constexpr int kTcBStages = 4;
+constexpr int kTcBStages = 2;
+constexpr int kTcTmemCols = 2 * kTcN;                 // ONE accumulator stage (a | b): the epilogue hands it back as soon as its
+                                                      // values sit in registers, so the next tile's MMAs run under the arithmetic
 constexpr int kTcSmemBytes = 2 * kTcTileA + kTcBStages * kTcTileB + 256;
 
 __host__ __device__ inline size_t tc_a_bytes(int n) { return (size_t)((n + 127) / 128) * kTcTileA; }
@@ -115,20 +118,22 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// tile schedule: a work item is a strip = (problem b, row block I of 128, S consecutive 64-column blocks J of the
-// upper triangle, J >= 2I).  CTA c walks items c, c + gridDim.x, ...; the producer lane and the epilogue warps iterate
-// the same sequence.
+// tile schedule: a work item is (problem b, row block I of 128, group g of S = 2^lgS consecutive 64-column blocks); the
+// strip of an item are the blocks J = max(2I, gS) .. min(nt64, (g+1)S) - 1 of the upper triangle (items whose group lies
+// below the diagonal are empty and skipped).  G = groups per row block rounded up to a power of two, so that an item
+// decodes with one division (per strip) and shifts.  CTA c walks items c, c + gridDim.x, ...; the TMA lane, the MMA lane
+// and the epilogue warps iterate the same sequence.
 // ------------------------------------------------------------------------------------------------
 struct TileIter {
-  int item, step, total, spp, S, nt, nt64;
+  int item, step, total, lgS, lgG, nt, nt64;
   int b, I, J, J1;
   bool first;
-  __device__ __forceinline__ void init(int start, int step_, int total_, int spp_, int S_, int n) {
+  __device__ __forceinline__ void init(int start, int step_, int total_, int lgS_, int lgG_, int n) {
     item = start - step_;
     step = step_;
     total = total_;
-    spp = spp_;
-    S = S_;
+    lgS = lgS_;
+    lgG = lgG_;
     nt = (n + kTile - 1) / kTile;
     nt64 = tc_nt64(n);
     b = I = 0;
@@ -141,31 +146,22 @@ struct TileIter {
       first = false;
       return true;
     }
-    item += step;
-    if (item >= total) return false;
-    b = item / spp;
-    int p = item - b * spp;
-    I = 0;
     while (true) {
-      const int ng = (nt64 - 2 * I + S - 1) / S;
-      if (p < ng) break;
-      p -= ng;
-      ++I;
+      item += step;
+      if (item >= total) return false;
+      const int rows = item >> lgG, g = item & ((1 << lgG) - 1);
+      b = rows / nt;
+      I = rows - b * nt;
+      const int lo = g << lgS;
+      J = max(2 * I, lo);
+      J1 = min(nt64, lo + (1 << lgS));
+      if (J < J1) break;
     }
-    J = 2 * I + p * S;
-    J1 = min(nt64, J + S);
     first = true;
     return true;
   }
   __device__ __forceinline__ bool last_of_strip() const { return J + 1 == J1; }
 };
-
-__host__ __device__ inline int tc_strips_per_problem(int n, int S) {
-  const int nt = (n + kTile - 1) / kTile, nt64 = tc_nt64(n);
-  int total = 0;
-  for (int I = 0; I < nt; ++I) total += (nt64 - 2 * I + S - 1) / S;
-  return total;
-}
 
 // packed FP32x2 (two pairs per instruction; FADD2 / FMUL2 / FFMA2)
 typedef unsigned long long f32x2;
@@ -212,14 +208,14 @@ struct TcConsts {
   f32x2 nc2, b4, kap, c0;  // -2 beta^2, beta^4, band slope, band offset (prep_kernel)
 };
 
-// 16 pairs (columns c0 .. c0+15 of the warp's 32; call with the upper half first).  Per pair, packed two at a time:
+// 8 pairs (columns c0 .. c0+7 of the warp's 32; call with the highest group first).  Per pair, packed two at a time:
 //   t = a - b, s = a + b, P = t^2 + beta^4, d = P - 2 beta^2 s  [= (g^2 - beta^2)(w - beta^2)],  band = kap P + c0,
 //   d_hi = d + band  (sign bit 1: surely an edge),   d_lo = d - band  (sign bit 0: surely not an edge)
 // = 7 FP32 lane operations, no MUFU, no compare; the two sign bits are funnel-shifted into the words.
-__device__ __forceinline__ void tc_sweep16(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const TcConsts& k,
-                                           uint32_t& whi, uint32_t& wlo) {
+__device__ __forceinline__ void tc_sweep8(const uint32_t (&ra)[8], const uint32_t (&rb)[8], const TcConsts& k,
+                                          uint32_t& whi, uint32_t& wlo) {
 #pragma unroll
-  for (int g = 7; g >= 0; --g) {
+  for (int g = 3; g >= 0; --g) {
     const f32x2 A = pk2(ra[2 * g], ra[2 * g + 1]), B = pk2(rb[2 * g], rb[2 * g + 1]);
     const f32x2 t = sub2(A, B), s = add2(A, B);
     const f32x2 P = fma2(t, t, k.b4);
@@ -258,13 +254,13 @@ enum {
   kBarAEmpty = 2,                         // [2]  MMA commit -> TMA: the strip's A tile has been read for the last time
   kBarBFull = 4,                          // [kTcBStages]  TMA -> MMA
   kBarBEmpty = kBarBFull + kTcBStages,    // [kTcBStages]  MMA commit -> TMA: stage may be overwritten
-  kBarTFull = kBarBEmpty + kTcBStages,    // [2]  MMA commit -> epilogue: accumulator stage ready
-  kBarTEmpty = kBarTFull + 2,             // [2]  epilogue (8 arrivals) -> MMA: accumulator stage drained
-  kNumBars = kBarTEmpty + 2
+  kBarTFull = kBarBEmpty + kTcBStages,    // MMA commit -> epilogue: accumulators ready
+  kBarTEmpty = kBarTFull + 1,             // epilogue (8 arrivals) -> MMA: accumulators are in registers
+  kNumBars = kBarTEmpty + 1
 };
 
 template <bool kVerify>
-__global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S, int spp, int total_items) {
+__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batch bt, int lgS, int lgG, int total_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcTileA + kTcBStages * kTcTileB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
@@ -275,93 +271,87 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = bt.n;
   if (tid == 0) {
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i >= kBarTEmpty ? kTcEpiWarps : 1);
+    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i == kBarTEmpty ? kTcEpiWarps : 1);
     mbar_fence_init();
   }
-  if (warp == kTcEpiWarps) tmem_alloc<256>(smem_u32(tmem_slot));
+  if (warp == kTcEpiWarps) tmem_alloc<kTcTmemCols>(smem_u32(tmem_slot));
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tbase = *tmem_slot;  // accumulator stage s: a at columns 128 s .. +63, b at 128 s + 64 .. +63
+  const uint32_t tbase = *tmem_slot;  // a at columns 0 .. 63, b at 64 .. 127
 
-  if (warp == kTcEpiWarps) {
-    // ================= producer: TMA loads (kTcBStages - 1 tiles ahead), MMA issue =================
-    if (lane == 0) {
+  if (warp >= kTcEpiWarps) {
+    // ================= producer warps: warp 8 lane 0 = TMA loads, warp 9 lane 0 = MMA issue =================
+    // Two threads in two warps: a load never has to wait behind an MMA that has not been issued yet, and each walks the
+    // tile sequence once.
+    if (warp == kTcEpiWarps && lane == 0) {
       const uint8_t* opnd = reinterpret_cast<const uint8_t*>(bt.opnd);
       const size_t per_problem = tc_a_bytes(n) + tc_b_bytes(n), a_bytes = tc_a_bytes(n);
-      TileIter ld, mm;
-      ld.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
-      mm.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
-      uint32_t n_loaded = 0, n_strips_loaded = 0, n_mma = 0, n_strips = 0, ap = 0;
-      int tc_b = -1;
+      TileIter ld;
+      ld.init(blockIdx.x, gridDim.x, total_items, lgS, lgG, n);
+      uint32_t n_loaded = 0, n_strips_loaded = 0;
+      int cur_b = -1;
       bool tc_ok = false;
-      auto next_tc = [&](TileIter& t) {  // next tile of a problem that takes the tensor-core path
-        while (t.next()) {
-          if (t.b != tc_b) {
-            tc_b = t.b;
-            tc_ok = bt.gc[t.b].use_tc != 0;
-          }
-          if (tc_ok) return true;
+      while (ld.next()) {
+        if (ld.b != cur_b) {
+          cur_b = ld.b;
+          tc_ok = bt.gc[ld.b].use_tc != 0;
         }
-        return false;
-      };
-      auto issue_load = [&](const TileIter& t) {
-        const uint32_t st = n_loaded % kTcBStages, use = n_loaded / kTcBStages;
-        if (use > 0) mbar_wait(bar(kBarBEmpty + st), (use - 1) & 1u);  // the MMAs that read this stage are complete
-        const uint8_t* pb = opnd + (size_t)t.b * per_problem;
-        if (t.first) {
+        if (!tc_ok) continue;
+        const uint8_t* pb = opnd + (size_t)ld.b * per_problem;
+        if (ld.first) {
           // A buffer (strip index & 1): wait until the strip that used it two strips ago has been read completely
           const uint32_t a = n_strips_loaded & 1u;
           if (n_strips_loaded >= 2) mbar_wait(bar(kBarAEmpty + a), ((n_strips_loaded >> 1) - 1) & 1u);
           mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
-          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
+          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)ld.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
           ++n_strips_loaded;
         }
+        const uint32_t st = n_loaded % kTcBStages, use = n_loaded / kTcBStages;
+        if (use > 0) mbar_wait(bar(kBarBEmpty + st), (use - 1) & 1u);  // the MMAs that read this stage are complete
         mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
-        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
+        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)ld.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
         ++n_loaded;
-      };
-      const uint32_t idesc = make_idesc_tf32(128, kTcN);
-      // The loads run ahead of the MMAs by at most kTcBStages - 1 tiles and at most one strip: this thread issues both,
-      // so a load may only wait for commits of MMAs that have ALREADY been issued (B stage of tile n_loaded - kTcBStages,
-      // A buffer of the strip before the previous one) — otherwise it would wait for itself.
-      bool pend = next_tc(ld);
-      auto can_load = [&]() {
-        return pend && (n_loaded - n_mma) < (uint32_t)(kTcBStages - 1) && (!ld.first || n_strips >= n_strips_loaded);
-      };
-      while (can_load()) {
-        issue_load(ld);
-        pend = next_tc(ld);
       }
-      while (next_tc(mm)) {
+    } else if (warp == kTcEpiWarps + 1 && lane == 0) {
+      TileIter mm;
+      mm.init(blockIdx.x, gridDim.x, total_items, lgS, lgG, n);
+      uint32_t n_mma = 0, n_strips = 0, ap = 0;
+      int cur_b = -1;
+      bool tc_ok = false;
+      const uint32_t idesc = make_idesc_tf32(128, kTcN);
+      // K-major, no swizzle: leading byte offset = distance of the two 16-byte K-chunks (planes), stride byte offset
+      // = distance of consecutive 8-row groups (128 B).  The start address sits in the low 14 bits (>> 4): the
+      // descriptors of the other buffers / clouds / K-steps are this one plus a constant.
+      const uint64_t descA = make_smem_desc(sA0, kTcPlaneA, 128), descB = make_smem_desc(sB0, kTcPlaneB, 128);
+      while (mm.next()) {
+        if (mm.b != cur_b) {
+          cur_b = mm.b;
+          tc_ok = bt.gc[mm.b].use_tc != 0;
+        }
+        if (!tc_ok) continue;
         const uint32_t st = n_mma % kTcBStages, use = n_mma / kTcBStages;
-        const uint32_t ts = n_mma & 1u, tuse = n_mma >> 1;
         if (mm.first) {
           ap = n_strips & 1u;
           mbar_wait(bar(kBarAFull + ap), (n_strips >> 1) & 1u);
           ++n_strips;
         }
         mbar_wait(bar(kBarBFull + st), use & 1u);
-        if (tuse > 0) mbar_wait(bar(kBarTEmpty + ts), (tuse - 1) & 1u);  // the epilogue has drained this accumulator stage
+        if (n_mma > 0) mbar_wait(bar(kBarTEmpty), (n_mma - 1) & 1u);  // the epilogue holds the previous tile in registers
         fence_after_sync();
-        // K-major, no swizzle: leading byte offset = distance of the two 16-byte K-chunks (planes), stride byte offset
-        // = distance of consecutive 8-row groups (128 B)
+        const uint64_t da0 = descA + (uint64_t)((ap * kTcTileA) >> 4), db0 = descB + (uint64_t)((st * kTcTileB) >> 4);
 #pragma unroll
         for (int cloud = 0; cloud < 2; ++cloud)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const uint64_t da = make_smem_desc(sA0 + ap * kTcTileA + cloud * kTcCloudA + s * 2 * kTcPlaneA, kTcPlaneA, 128);
-            const uint64_t db = make_smem_desc(sB0 + st * kTcTileB + cloud * kTcCloudB + s * 2 * kTcPlaneB, kTcPlaneB, 128);
-            mma_tf32(tbase + 128u * ts + (uint32_t)kTcN * cloud, da, db, idesc, s > 0);
+          for (int k = 0; k < 3; ++k) {
+            const uint64_t da = da0 + (uint64_t)((cloud * kTcCloudA + k * 2 * kTcPlaneA) >> 4);
+            const uint64_t db = db0 + (uint64_t)((cloud * kTcCloudB + k * 2 * kTcPlaneB) >> 4);
+            mma_tf32(tbase + (uint32_t)kTcN * cloud, da, db, idesc, k > 0);
           }
         mma_commit(bar(kBarBEmpty + st));
         if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
-        mma_commit(bar(kBarTFull + ts));
+        mma_commit(bar(kBarTFull));
         ++n_mma;
-        while (can_load()) {
-          issue_load(ld);
-          pend = next_tc(ld);
-        }
       }
     }
     __syncwarp();
@@ -370,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     TileIter ti;
-    ti.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
+    ti.init(blockIdx.x, gridDim.x, total_items, lgS, lgG, n);
     uint32_t n_t = 0;
     int rdeg = 0;
     const int P32 = pitch32(n);
@@ -403,27 +393,34 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
         row_edge = I * kTile + kTile > n;  // some rows of the block lie past n
       }
       const int j0 = J * kTcN + 32 * h;
-      const uint32_t ts = n_t & 1u;
-      mbar_wait(bar(kBarTFull + ts), (n_t >> 1) & 1u);
+      mbar_wait(bar(kBarTFull), n_t & 1u);
       fence_after_sync();
-      const uint32_t ta = tbase + lane_base + 128u * ts + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
-      // ---- sweep: whi bit k = pair (i, j0+k) surely an edge, wlo bit k = not surely a non-edge.  The second half of the
-      // accumulators is in flight while the first is evaluated; the stage goes back to the MMA issuer as soon as the
-      // warp's 2 x 32 x 32 values sit in registers.
+      const uint32_t ta = tbase + lane_base + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
+      // ---- sweep: whi bit k = pair (i, j0+k) surely an edge, wlo bit k = not surely a non-edge.  Eight columns at a
+      // time, the next eight in flight; the accumulators go back to the MMA issuer as soon as the warp's 2 x 32 x 32
+      // values have been read (the arithmetic of the last group and everything after it overlaps the next tile's MMAs).
       uint32_t whi = 0u, wlo = 0u;
       {
-        uint32_t a1[16], b1[16], a0[16], b0[16];
-        tmem_ld16(ta + 16u, a1);
-        tmem_ld16(tb + 16u, b1);
+        uint32_t a0[8], b0[8], a1[8], b1[8];
+        tmem_ld8(ta + 24u, a1);
+        tmem_ld8(tb + 24u, b1);
         tmem_wait_ld();
-        tmem_ld16(ta, a0);
-        tmem_ld16(tb, b0);
-        tc_sweep16(a1, b1, kc, whi, wlo);
+        tmem_ld8(ta + 16u, a0);
+        tmem_ld8(tb + 16u, b0);
+        tc_sweep8(a1, b1, kc, whi, wlo);
+        tmem_wait_ld();
+        tmem_ld8(ta + 8u, a1);
+        tmem_ld8(tb + 8u, b1);
+        tc_sweep8(a0, b0, kc, whi, wlo);
+        tmem_wait_ld();
+        tmem_ld8(ta, a0);
+        tmem_ld8(tb, b0);
+        tc_sweep8(a1, b1, kc, whi, wlo);
         tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kBarTEmpty + ts));
-        tc_sweep16(a0, b0, kc, whi, wlo);
+        if (lane == 0) mbar_arrive(bar(kBarTEmpty));
+        tc_sweep8(a0, b0, kc, whi, wlo);
       }
       // validity of the pairs of this thread: columns < n, row < n, i != j (interior tiles: everything valid)
       uint32_t vmask = 0xffffffffu;
@@ -512,7 +509,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == kTcEpiWarps) tmem_dealloc<256>(tbase);
+  if (warp == kTcEpiWarps) tmem_dealloc<kTcTmemCols>(tbase);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -548,6 +545,13 @@ __global__ void __launch_bounds__(256) tc_patch_kernel(Batch bt) {
   }
 }
 
+static int tc_strips_per_problem(int n, int S) {  // non-empty strips of one problem for strip length S
+  const int nt = (n + kTile - 1) / kTile, nt64 = tc_nt64(n);
+  int total = 0;
+  for (int I = 0; I < nt; ++I) total += (nt64 - 2 * I + S - 1) / S;
+  return total;
+}
+
 int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   static bool attr_done_dev[64] = {};
   int dev = 0;
@@ -555,23 +559,28 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   if (!attr_done_dev[dev & 63]) {
     cudaFuncSetAttribute(graph_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     cudaFuncSetAttribute(graph_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    // three CTAs of 72 KB per SM: the whole 228 KB as shared memory
+    cudaFuncSetAttribute(graph_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(graph_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done_dev[dev & 63] = true;
   }
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 pg((unsigned)nt, (unsigned)bt.B);
   cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);
   tc_prep_kernel<<<pg, 128, 0, st>>>(bt);
-  // strip length (in 64-column tiles): long strips amortise the A tile, short ones balance small batches
-  const int ctas = 2 * num_sms;
-  int S = 16;
-  while (S > 1 && (long long)bt.B * tc_strips_per_problem(bt.n, S) < 4LL * ctas) S >>= 1;
-  const int spp = tc_strips_per_problem(bt.n, S);
-  const long long total = (long long)bt.B * spp;
+  // strip length (in 64-column tiles, a power of two): long strips amortise the A tile, short ones balance small batches
+  const int ctas = kTcCtasPerSm * num_sms;
+  const int nt64 = tc_nt64(bt.n);
+  int lgS = 4;
+  while (lgS > 0 && (long long)bt.B * tc_strips_per_problem(bt.n, 1 << lgS) < 4LL * ctas) --lgS;
+  int lgG = 0;
+  while (((nt64 + (1 << lgS) - 1) >> lgS) > (1 << lgG)) ++lgG;
+  const long long total = ((long long)bt.B * nt) << lgG;
   const int grid = (int)(total < ctas ? total : ctas);
   if (bt.flags_dbg & 2u)
-    graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
+    graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, lgS, lgG, (int)total);
   else
-    graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
+    graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, lgS, lgG, (int)total);
   tc_patch_kernel<<<4 * num_sms, 256, 0, st>>>(bt);
   cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);  // the strip kernel (other problems) queues next
   return 3;

@@ -39,7 +39,9 @@ constexpr int kExactThreads = 256;
 #define TZR_EXACT_MIN_BLOCKS 3  // CTAs per SM the exact kernel is compiled for (80 registers; 2 -> 128)
 #endif
 constexpr int kExactWarps = kExactThreads / 32;
+#ifdef TZR_BLOCK_BOUND
 constexpr int kBlkBatch = 16; // block colour bound: row words in flight per lane (x2, ping-pong)
+#endif
 constexpr int kYU = 2;        // colouring: bitset words per lane whose row loads are issued together
 constexpr int kSpecCand = 8;  // colouring: candidates resolved per round trip to the bitset (see node_colour)
 
@@ -1026,7 +1028,14 @@ __device__ int node_colour(WarpCtx& c, int csz) {
 // blocks are different colours, so the sum over the blocks is a valid (weaker) colour bound: ~0.085 colours per vertex
 // at 15 % density and 128-vertex blocks against ~0.04 for the full greedy colouring — enough whenever
 // |P| is below ~12x the incumbent size, at a fraction of the row traffic and without the dependent round trips.
-__device__ bool node_block_bound(WarpCtx& c, int csz) {
+// Measured on B200 (C3, one problem, scripts/gpu_r2_s2_clique_ab.sh): the search is FASTER without this bound (18.7 ms vs
+// 20.0 ms with the counters of debug flag 4 on), and inlined into the ~10 k-instruction search kernel the build faults
+// with "illegal instruction" at a warp collective (the kernel runs out of convergence-barrier registers; out of line it
+// is correct).  So it is compiled only with EXTRA=-DTZR_BLOCK_BOUND, out of line, for A/B runs.
+#ifndef TZR_BLOCK_BOUND
+__device__ __forceinline__ bool node_block_bound(WarpCtx&, int) { return false; }
+#else
+__noinline__ __device__ bool node_block_bound(WarpCtx& c, int csz) {
   const int W = c.W, lane = c.lane, S = c.blk;
   const int kmin = *c.Lp + c.strict - csz;
   if (S == 0 || kmin <= 1 || (c.bt->flags_dbg & 4096u)) return false;  // 4096: A/B switch (bench/profiling)
@@ -1178,6 +1187,7 @@ __device__ bool node_block_bound(WarpCtx& c, int csz) {
   }
   return colours < kmin;
 }
+#endif  // TZR_BLOCK_BOUND
 
 // Offer the clique cv[0..csz) as incumbent.  Larger wins; on equal size the lexicographically smaller
 // sorted index set wins (== the set that owns the lowest vertex of the symmetric difference), which makes
