@@ -35,7 +35,7 @@ namespace tzr {
 using namespace tc;
 
 constexpr int kTcEpiWarps = 8;                        // warp w: TMEM lanes 32*(w&3).., columns 32*(w>>2)..
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 2);    // + warp 8: one lane drives the TMA engine, + warp 9: one lane issues the MMAs
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);    // + 1 producer warp (TMA + MMA issue by one elected lane): 72 registers at 3 CTAs per SM
 constexpr int kTcCtasPerSm = 3;                       // 24 epilogue warps per SM: the epilogue is latency-bound per warp
 constexpr int kTcN = 64;                              // columns of one tile (MMA N)
 constexpr int kTcPlaneA = 128 * 16;                   // A role: 128 rows x 4 tf32 per plane
@@ -118,49 +118,59 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// tile schedule: a work item is (problem b, row block I of 128, group g of S = 2^lgS consecutive 64-column blocks); the
-// strip of an item are the blocks J = max(2I, gS) .. min(nt64, (g+1)S) - 1 of the upper triangle (items whose group lies
-// below the diagonal are empty and skipped).  G = groups per row block rounded up to a power of two, so that an item
-// decodes with one division (per strip) and shifts.  CTA c walks items c, c + gridDim.x, ...; the TMA lane, the MMA lane
-// and the epilogue warps iterate the same sequence.
+// tile schedule: the tiles of the batch in the order (problem b, row block I of 128, 64-column block J = 2I .. nt64-1 of
+// the upper triangle) are cut into gridDim.x contiguous ranges of equal length (+-1 tile): perfectly balanced whatever
+// the row lengths are (a round-robin deal of strips aliased with the strip-length pattern: measured 2x between the
+// busiest and the idlest SM), and a CTA walks whole rows, so the A tile of a row block is fetched once.  A "strip" is a
+// maximal run of tiles of one row block inside a range.  The producer lane and the epilogue warps iterate the same
+// sequence.
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int tc_tiles_per_problem(int n) {
+  const int nt = (n + kTile - 1) / kTile;
+  return nt * tc_nt64(n) - nt * (nt - 1);
+}
+
 struct TileIter {
-  int item, step, total, lgS, lgG, nt, nt64;
-  int b, I, J, J1;
-  bool first;
-  __device__ __forceinline__ void init(int start, int step_, int total_, int lgS_, int lgG_, int n) {
-    item = start - step_;
-    step = step_;
-    total = total_;
-    lgS = lgS_;
-    lgG = lgG_;
+  int remaining, nt, nt64;
+  int b, I, J;
+  bool first, started;
+  __device__ __forceinline__ void init(int cta, int ctas, long long total_tiles, int n) {
     nt = (n + kTile - 1) / kTile;
     nt64 = tc_nt64(n);
-    b = I = 0;
-    J = J1 = 0;
+    const long long t0 = total_tiles * cta / ctas, t1 = total_tiles * (cta + 1) / ctas;
+    remaining = (int)(t1 - t0);
+    const int tpp = tc_tiles_per_problem(n);
+    b = (int)(t0 / tpp);
+    int r = (int)(t0 - (long long)b * tpp);
+    I = 0;
+    while (r >= nt64 - 2 * I) {
+      r -= nt64 - 2 * I;
+      ++I;
+    }
+    J = 2 * I + r;
     first = false;
+    started = false;
   }
   __device__ __forceinline__ bool next() {
-    if (J + 1 < J1) {
-      ++J;
-      first = false;
+    if (remaining == 0) return false;
+    --remaining;
+    if (!started) {
+      started = true;
+      first = true;
       return true;
     }
-    while (true) {
-      item += step;
-      if (item >= total) return false;
-      const int rows = item >> lgG, g = item & ((1 << lgG) - 1);
-      b = rows / nt;
-      I = rows - b * nt;
-      const int lo = g << lgS;
-      J = max(2 * I, lo);
-      J1 = min(nt64, lo + (1 << lgS));
-      if (J < J1) break;
+    first = false;
+    if (++J == nt64) {
+      if (++I == nt) {
+        I = 0;
+        ++b;
+      }
+      J = 2 * I;
+      first = true;
     }
-    first = true;
     return true;
   }
-  __device__ __forceinline__ bool last_of_strip() const { return J + 1 == J1; }
+  __device__ __forceinline__ bool last_of_strip() const { return J + 1 == nt64 || remaining == 0; }
 };
 
 // packed FP32x2 (two pairs per instruction; FADD2 / FMUL2 / FFMA2)
@@ -260,7 +270,7 @@ enum {
 };
 
 template <bool kVerify>
-__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batch bt, int lgS, int lgG, int total_items) {
+__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batch bt, long long total_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcTileA + kTcBStages * kTcTileB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
@@ -280,56 +290,64 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;  // a at columns 0 .. 63, b at 64 .. 127
 
-  if (warp >= kTcEpiWarps) {
-    // ================= producer warps: warp 8 lane 0 = TMA loads, warp 9 lane 0 = MMA issue =================
-    // Two threads in two warps: a load never has to wait behind an MMA that has not been issued yet, and each walks the
-    // tile sequence once.
-    if (warp == kTcEpiWarps && lane == 0) {
+  if (warp == kTcEpiWarps) {
+    // ================= producer: TMA loads (up to kTcBStages tiles ahead), MMA issue =================
+    // One thread does both (a tenth warp would cost the 72-register budget of 3 CTAs per SM: measured, the spills of the
+    // 64-register build sat on the epilogue's critical path), so a load may only wait for commits of MMAs that have
+    // ALREADY been issued (B stage of tile n_loaded - kTcBStages, A buffer of the strip before the previous one): the
+    // loads run at most kTcBStages tiles and one strip ahead of the MMAs.
+    if (lane == 0) {
       const uint8_t* opnd = reinterpret_cast<const uint8_t*>(bt.opnd);
       const size_t per_problem = tc_a_bytes(n) + tc_b_bytes(n), a_bytes = tc_a_bytes(n);
-      TileIter ld;
-      ld.init(blockIdx.x, gridDim.x, total_items, lgS, lgG, n);
-      uint32_t n_loaded = 0, n_strips_loaded = 0;
-      int cur_b = -1;
-      bool tc_ok = false;
-      while (ld.next()) {
-        if (ld.b != cur_b) {
-          cur_b = ld.b;
-          tc_ok = bt.gc[ld.b].use_tc != 0;
+      TileIter ld, mm;
+      ld.init(blockIdx.x, gridDim.x, total_tiles, n);
+      mm.init(blockIdx.x, gridDim.x, total_tiles, n);
+      uint32_t n_loaded = 0, n_strips_loaded = 0, n_mma = 0, n_strips = 0, ap = 0;
+      int ld_b = -1, mm_b = -1;
+      bool ld_ok = false, mm_ok = false;
+      auto next_tc = [&](TileIter& t, int& cur_b, bool& ok) {  // next tile of a problem that takes the tensor-core path
+        while (t.next()) {
+          if (t.b != cur_b) {
+            cur_b = t.b;
+            ok = bt.gc[t.b].use_tc != 0;
+          }
+          if (ok) return true;
         }
-        if (!tc_ok) continue;
-        const uint8_t* pb = opnd + (size_t)ld.b * per_problem;
-        if (ld.first) {
+        return false;
+      };
+      auto issue_load = [&](const TileIter& t) {
+        const uint32_t st = n_loaded % kTcBStages, use = n_loaded / kTcBStages;
+        if (use > 0) mbar_wait(bar(kBarBEmpty + st), (use - 1) & 1u);  // the MMAs that read this stage are complete
+        const uint8_t* pb = opnd + (size_t)t.b * per_problem;
+        if (t.first) {
           // A buffer (strip index & 1): wait until the strip that used it two strips ago has been read completely
           const uint32_t a = n_strips_loaded & 1u;
           if (n_strips_loaded >= 2) mbar_wait(bar(kBarAEmpty + a), ((n_strips_loaded >> 1) - 1) & 1u);
           mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
-          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)ld.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
+          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
           ++n_strips_loaded;
         }
-        const uint32_t st = n_loaded % kTcBStages, use = n_loaded / kTcBStages;
-        if (use > 0) mbar_wait(bar(kBarBEmpty + st), (use - 1) & 1u);  // the MMAs that read this stage are complete
         mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
-        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)ld.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
+        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
         ++n_loaded;
-      }
-    } else if (warp == kTcEpiWarps + 1 && lane == 0) {
-      TileIter mm;
-      mm.init(blockIdx.x, gridDim.x, total_items, lgS, lgG, n);
-      uint32_t n_mma = 0, n_strips = 0, ap = 0;
-      int cur_b = -1;
-      bool tc_ok = false;
+      };
       const uint32_t idesc = make_idesc_tf32(128, kTcN);
       // K-major, no swizzle: leading byte offset = distance of the two 16-byte K-chunks (planes), stride byte offset
       // = distance of consecutive 8-row groups (128 B).  The start address sits in the low 14 bits (>> 4): the
       // descriptors of the other buffers / clouds / K-steps are this one plus a constant.
       const uint64_t descA = make_smem_desc(sA0, kTcPlaneA, 128), descB = make_smem_desc(sB0, kTcPlaneB, 128);
-      while (mm.next()) {
-        if (mm.b != cur_b) {
-          cur_b = mm.b;
-          tc_ok = bt.gc[mm.b].use_tc != 0;
-        }
-        if (!tc_ok) continue;
+      bool pend = next_tc(ld, ld_b, ld_ok);
+      // tile n_loaded goes to the stage tile n_loaded - kTcBStages was read from: its MMAs must have been issued (the wait
+      // inside issue_load then only lasts until they complete); a new strip's A tile needs the strip before the previous
+      // one to have been issued completely, i.e. the previous one to have started
+      auto can_load = [&]() {
+        return pend && (n_loaded - n_mma) < (uint32_t)kTcBStages && (!ld.first || n_strips >= n_strips_loaded);
+      };
+      while (can_load()) {
+        issue_load(ld);
+        pend = next_tc(ld, ld_b, ld_ok);
+      }
+      while (next_tc(mm, mm_b, mm_ok)) {
         const uint32_t st = n_mma % kTcBStages, use = n_mma / kTcBStages;
         if (mm.first) {
           ap = n_strips & 1u;
@@ -352,6 +370,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
         if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
         mma_commit(bar(kBarTFull));
         ++n_mma;
+        while (can_load()) {
+          issue_load(ld);
+          pend = next_tc(ld, ld_b, ld_ok);
+        }
       }
     }
     __syncwarp();
@@ -360,7 +382,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     TileIter ti;
-    ti.init(blockIdx.x, gridDim.x, total_items, lgS, lgG, n);
+    ti.init(blockIdx.x, gridDim.x, total_tiles, n);
     uint32_t n_t = 0;
     int rdeg = 0;
     const int P32 = pitch32(n);
@@ -368,9 +390,6 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
     kc.nc2 = kc.b4 = kc.kap = kc.c0 = pk2f(0.f, 0.f);
     const GraphConsts* gcp = bt.gc;
     bool use_tc = false;
-    uint32_t* adj32 = nullptr;  // bitset of the strip's problem
-    uint32_t* rowp = nullptr;   // row i of it
-    int* degp = nullptr;
     int i = 0;
     bool row_ok = false, row_edge = false;
     while (ti.next()) {
@@ -386,9 +405,6 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
         kc.kap = pk2f(gcp->tc_kap, gcp->tc_kap);
         kc.c0 = pk2f(gcp->tc_c0, gcp->tc_c0);
         i = I * kTile + 32 * q + lane;
-        adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)ti.b * n * P32;
-        rowp = adj32 + (size_t)i * P32;
-        degp = bt.deg + (size_t)ti.b * n;
         row_ok = i < n;
         row_edge = I * kTile + kTile > n;  // some rows of the block lie past n
       }
@@ -490,8 +506,10 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
           }
         }
       }
+      uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)ti.b * ((size_t)n * P32);  // bitset of the problem
+      int* degp = bt.deg + (size_t)ti.b * n;
       rdeg += __popc(word);
-      if (row_ok) rowp[2 * J + h] = word;
+      if (row_ok) adj32[(size_t)i * P32 + 2 * J + h] = word;
       if (!diag) {  // transposed half: lane l holds column j0+l over rows I*128 + 32q .. +31
         const uint32_t colw = tc_transpose32(word, lane);
         const int jc = j0 + lane;
@@ -545,13 +563,6 @@ __global__ void __launch_bounds__(256) tc_patch_kernel(Batch bt) {
   }
 }
 
-static int tc_strips_per_problem(int n, int S) {  // non-empty strips of one problem for strip length S
-  const int nt = (n + kTile - 1) / kTile, nt64 = tc_nt64(n);
-  int total = 0;
-  for (int I = 0; I < nt; ++I) total += (nt64 - 2 * I + S - 1) / S;
-  return total;
-}
-
 int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   static bool attr_done_dev[64] = {};
   int dev = 0;
@@ -568,19 +579,13 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   dim3 pg((unsigned)nt, (unsigned)bt.B);
   cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);
   tc_prep_kernel<<<pg, 128, 0, st>>>(bt);
-  // strip length (in 64-column tiles, a power of two): long strips amortise the A tile, short ones balance small batches
   const int ctas = kTcCtasPerSm * num_sms;
-  const int nt64 = tc_nt64(bt.n);
-  int lgS = 4;
-  while (lgS > 0 && (long long)bt.B * tc_strips_per_problem(bt.n, 1 << lgS) < 4LL * ctas) --lgS;
-  int lgG = 0;
-  while (((nt64 + (1 << lgS) - 1) >> lgS) > (1 << lgG)) ++lgG;
-  const long long total = ((long long)bt.B * nt) << lgG;
+  const long long total = (long long)bt.B * tc_tiles_per_problem(bt.n);
   const int grid = (int)(total < ctas ? total : ctas);
   if (bt.flags_dbg & 2u)
-    graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, lgS, lgG, (int)total);
+    graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, total);
   else
-    graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, lgS, lgG, (int)total);
+    graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, total);
   tc_patch_kernel<<<4 * num_sms, 256, 0, st>>>(bt);
   cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);  // the strip kernel (other problems) queues next
   return 3;
