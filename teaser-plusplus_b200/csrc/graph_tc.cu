@@ -35,17 +35,19 @@ namespace tzr {
 using namespace tc;
 
 constexpr int kTcEpiWarps = 8;                        // warp w: TMEM lanes 32*(w&3).., columns 32*(w>>2)..
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);    // + 1 producer warp (TMA + MMA issue by one elected lane): 72 registers at 3 CTAs per SM
-constexpr int kTcCtasPerSm = 3;                       // 24 epilogue warps per SM: the epilogue is latency-bound per warp
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);    // + 1 producer warp (TMA + MMA issue by one elected lane)
+constexpr int kTcCtasPerSm = 2;                       // 2 x 256 TMEM columns = all of an SM's tensor memory
 constexpr int kTcN = 64;                              // columns of one tile (MMA N)
 constexpr int kTcPlaneA = 128 * 16;                   // A role: 128 rows x 4 tf32 per plane
 constexpr int kTcPlaneB = kTcN * 16;                  // B role: 64 rows x 4 tf32 per plane
 constexpr int kTcCloudA = 6 * kTcPlaneA, kTcCloudB = 6 * kTcPlaneB;   // 6 planes = K 24
 constexpr int kTcTileA = 2 * kTcCloudA;               // src + dst: 24 KB per 128-row block
 constexpr int kTcTileB = 2 * kTcCloudB;               // 12 KB per 64-column block
-constexpr int kTcBStages = 2;
-constexpr int kTcTmemCols = 2 * kTcN;                 // ONE accumulator stage (a | b): the epilogue hands it back as soon as its
-                                                      // values sit in registers, so the next tile's MMAs run under the arithmetic
+constexpr int kTcBStages = 4;
+constexpr int kTcTStages = 2;                         // accumulator stages: the producer's per-tile latency (its ~130-instruction
+                                                      // issue sequence shares a scheduler with busy epilogue warps) stays off
+                                                      // the epilogue's critical path only with a whole tile of slack
+constexpr int kTcTmemCols = kTcTStages * 2 * kTcN;    // per stage: a at columns 0 .. 63, b at 64 .. 127
 constexpr int kTcSmemBytes = 2 * kTcTileA + kTcBStages * kTcTileB + 256;
 
 __host__ __device__ inline size_t tc_a_bytes(int n) { return (size_t)((n + 127) / 128) * kTcTileA; }
@@ -264,9 +266,9 @@ enum {
   kBarAEmpty = 2,                         // [2]  MMA commit -> TMA: the strip's A tile has been read for the last time
   kBarBFull = 4,                          // [kTcBStages]  TMA -> MMA
   kBarBEmpty = kBarBFull + kTcBStages,    // [kTcBStages]  MMA commit -> TMA: stage may be overwritten
-  kBarTFull = kBarBEmpty + kTcBStages,    // MMA commit -> epilogue: accumulators ready
-  kBarTEmpty = kBarTFull + 1,             // epilogue (8 arrivals) -> MMA: accumulators are in registers
-  kNumBars = kBarTEmpty + 1
+  kBarTFull = kBarBEmpty + kTcBStages,    // [kTcTStages]  MMA commit -> epilogue: accumulator stage ready
+  kBarTEmpty = kBarTFull + kTcTStages,    // [kTcTStages]  epilogue (8 arrivals) -> MMA: the stage's values are in registers
+  kNumBars = kBarTEmpty + kTcTStages
 };
 
 template <bool kVerify>
@@ -281,22 +283,25 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = bt.n;
   if (tid == 0) {
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i == kBarTEmpty ? kTcEpiWarps : 1);
+    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i >= kBarTEmpty ? kTcEpiWarps : 1);
     mbar_fence_init();
   }
   if (warp == kTcEpiWarps) tmem_alloc<kTcTmemCols>(smem_u32(tmem_slot));
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tbase = *tmem_slot;  // a at columns 0 .. 63, b at 64 .. 127
+  const uint32_t tbase = *tmem_slot;  // accumulator stage s: a at columns 128 s .. +63, b at 128 s + 64 .. +63
 
   if (warp == kTcEpiWarps) {
     // ================= producer: TMA loads (up to kTcBStages tiles ahead), MMA issue =================
-    // One thread does both (a tenth warp would cost the 72-register budget of 3 CTAs per SM: measured, the spills of the
+    // One warp does both (a tenth warp would cost the 72-register budget of 3 CTAs per SM: measured, the spills of the
     // 64-register build sat on the epilogue's critical path), so a load may only wait for commits of MMAs that have
     // ALREADY been issued (B stage of tile n_loaded - kTcBStages, A buffer of the strip before the previous one): the
     // loads run at most kTcBStages tiles and one strip ahead of the MMAs.
-    if (lane == 0) {
+    // All 32 lanes walk the schedule (warp-uniform values live in uniform registers: no per-MMA broadcast loops), lane 0
+    // alone issues the copies, the MMAs and the commits.
+    {
+      const bool issuer = lane == 0;
       const uint8_t* opnd = reinterpret_cast<const uint8_t*>(bt.opnd);
       const size_t per_problem = tc_a_bytes(n) + tc_b_bytes(n), a_bytes = tc_a_bytes(n);
       TileIter ld, mm;
@@ -323,12 +328,16 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
           // A buffer (strip index & 1): wait until the strip that used it two strips ago has been read completely
           const uint32_t a = n_strips_loaded & 1u;
           if (n_strips_loaded >= 2) mbar_wait(bar(kBarAEmpty + a), ((n_strips_loaded >> 1) - 1) & 1u);
-          mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
-          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
+          if (issuer) {
+            mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
+            bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
+          }
           ++n_strips_loaded;
         }
-        mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
-        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
+        if (issuer) {
+          mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
+          bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
+        }
         ++n_loaded;
       };
       const uint32_t idesc = make_idesc_tf32(128, kTcN);
@@ -355,20 +364,23 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
           ++n_strips;
         }
         mbar_wait(bar(kBarBFull + st), use & 1u);
-        if (n_mma > 0) mbar_wait(bar(kBarTEmpty), (n_mma - 1) & 1u);  // the epilogue holds the previous tile in registers
-        fence_after_sync();
+        // Everything the MMAs need is formed BEFORE the wait for the accumulators: this thread shares its scheduler with six
+        // busy epilogue warps (one instruction every ~10-15 clk), and whatever sits between that wait and the last commit is
+        // serial time in which all eight epilogue warps of the CTA wait for the next tile (measured: 134 instructions there
+        // cost 35 % of the kernel).
         const uint64_t da0 = descA + (uint64_t)((ap * kTcTileA) >> 4), db0 = descB + (uint64_t)((st * kTcTileB) >> 4);
+        const uint32_t ts = n_mma % kTcTStages, tuse = n_mma / kTcTStages;
+        if (tuse > 0) mbar_wait(bar(kBarTEmpty + ts), (tuse - 1) & 1u);  // the epilogue has this stage's previous tile in registers
+        fence_after_sync();
+        if (issuer) {
 #pragma unroll
-        for (int cloud = 0; cloud < 2; ++cloud)
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const uint64_t da = da0 + (uint64_t)((cloud * kTcCloudA + k * 2 * kTcPlaneA) >> 4);
-            const uint64_t db = db0 + (uint64_t)((cloud * kTcCloudB + k * 2 * kTcPlaneB) >> 4);
-            mma_tf32(tbase + (uint32_t)kTcN * cloud, da, db, idesc, k > 0);
-          }
-        mma_commit(bar(kBarBEmpty + st));
-        if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
-        mma_commit(bar(kBarTFull));
+          for (int c = 0; c < 6; ++c)
+            mma_tf32(tbase + 128u * ts + (uint32_t)kTcN * (c / 3), da0 + (uint64_t)(((c / 3) * kTcCloudA + (c % 3) * 2 * kTcPlaneA) >> 4),
+                     db0 + (uint64_t)(((c / 3) * kTcCloudB + (c % 3) * 2 * kTcPlaneB) >> 4), idesc, (c % 3) > 0);
+          mma_commit(bar(kBarBEmpty + st));
+          if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
+          mma_commit(bar(kBarTFull + ts));
+        }
         ++n_mma;
         while (can_load()) {
           issue_load(ld);
@@ -409,34 +421,29 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
         row_edge = I * kTile + kTile > n;  // some rows of the block lie past n
       }
       const int j0 = J * kTcN + 32 * h;
-      mbar_wait(bar(kBarTFull), n_t & 1u);
+      const uint32_t ts = n_t % kTcTStages;
+      mbar_wait(bar(kBarTFull + ts), (n_t / kTcTStages) & 1u);
       fence_after_sync();
-      const uint32_t ta = tbase + lane_base + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
-      // ---- sweep: whi bit k = pair (i, j0+k) surely an edge, wlo bit k = not surely a non-edge.  Eight columns at a
-      // time, the next eight in flight; the accumulators go back to the MMA issuer as soon as the warp's 2 x 32 x 32
-      // values have been read (the arithmetic of the last group and everything after it overlaps the next tile's MMAs).
+      const uint32_t ta = tbase + lane_base + 128u * ts + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
+      // ---- sweep: whi bit k = pair (i, j0+k) surely an edge, wlo bit k = not surely a non-edge.  The second half of the
+      // accumulators is in flight while the first is evaluated; the stage goes back to the MMA issuer as soon as the
+      // warp's 2 x 32 x 32 values sit in registers.
       uint32_t whi = 0u, wlo = 0u;
       {
-        uint32_t a0[8], b0[8], a1[8], b1[8];
-        tmem_ld8(ta + 24u, a1);
-        tmem_ld8(tb + 24u, b1);
+        uint32_t a1[16], b1[16], a0[16], b0[16];
+        tmem_ld16(ta + 16u, a1);
+        tmem_ld16(tb + 16u, b1);
         tmem_wait_ld();
-        tmem_ld8(ta + 16u, a0);
-        tmem_ld8(tb + 16u, b0);
-        tc_sweep8(a1, b1, kc, whi, wlo);
-        tmem_wait_ld();
-        tmem_ld8(ta + 8u, a1);
-        tmem_ld8(tb + 8u, b1);
-        tc_sweep8(a0, b0, kc, whi, wlo);
-        tmem_wait_ld();
-        tmem_ld8(ta, a0);
-        tmem_ld8(tb, b0);
-        tc_sweep8(a1, b1, kc, whi, wlo);
+        tmem_ld16(ta, a0);
+        tmem_ld16(tb, b0);
+        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a1[8]), reinterpret_cast<const uint32_t(&)[8]>(b1[8]), kc, whi, wlo);
+        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a1[0]), reinterpret_cast<const uint32_t(&)[8]>(b1[0]), kc, whi, wlo);
         tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kBarTEmpty));
-        tc_sweep8(a0, b0, kc, whi, wlo);
+        if (lane == 0) mbar_arrive(bar(kBarTEmpty + ts));
+        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a0[8]), reinterpret_cast<const uint32_t(&)[8]>(b0[8]), kc, whi, wlo);
+        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a0[0]), reinterpret_cast<const uint32_t(&)[8]>(b0[0]), kc, whi, wlo);
       }
       // validity of the pairs of this thread: columns < n, row < n, i != j (interior tiles: everything valid)
       uint32_t vmask = 0xffffffffu;
@@ -570,7 +577,7 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   if (!attr_done_dev[dev & 63]) {
     cudaFuncSetAttribute(graph_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     cudaFuncSetAttribute(graph_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    // three CTAs of 72 KB per SM: the whole 228 KB as shared memory
+    // two CTAs of 96 KB per SM
     cudaFuncSetAttribute(graph_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(graph_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done_dev[dev & 63] = true;
