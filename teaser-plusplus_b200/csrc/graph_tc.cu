@@ -36,7 +36,6 @@ using namespace tc;
 
 constexpr int kTcEpiWarps = 8;                        // warp w: TMEM lanes 32*(w&3).., columns 32*(w>>2)..
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 1);    // + 1 producer warp (TMA + MMA issue by one elected lane)
-constexpr int kTcCtasPerSm = 2;                       // 2 x 256 TMEM columns = all of an SM's tensor memory
 constexpr int kTcN = 64;                              // columns of one tile (MMA N)
 constexpr int kTcPlaneA = 128 * 16;                   // A role: 128 rows x 4 tf32 per plane
 constexpr int kTcPlaneB = kTcN * 16;                  // B role: 64 rows x 4 tf32 per plane
@@ -44,10 +43,6 @@ constexpr int kTcCloudA = 6 * kTcPlaneA, kTcCloudB = 6 * kTcPlaneB;   // 6 plane
 constexpr int kTcTileA = 2 * kTcCloudA;               // src + dst: 24 KB per 128-row block
 constexpr int kTcTileB = 2 * kTcCloudB;               // 12 KB per 64-column block
 constexpr int kTcBStages = 4;
-constexpr int kTcTStages = 2;                         // accumulator stages: the producer's per-tile latency (its ~130-instruction
-                                                      // issue sequence shares a scheduler with busy epilogue warps) stays off
-                                                      // the epilogue's critical path only with a whole tile of slack
-constexpr int kTcTmemCols = kTcTStages * 2 * kTcN;    // per stage: a at columns 0 .. 63, b at 64 .. 127
 constexpr int kTcSmemBytes = 2 * kTcTileA + kTcBStages * kTcTileB + 256;
 
 __host__ __device__ inline size_t tc_a_bytes(int n) { return (size_t)((n + 127) / 128) * kTcTileA; }
@@ -120,60 +115,57 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(Batch bt) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// tile schedule: the tiles of the batch in the order (problem b, row block I of 128, 64-column block J = 2I .. nt64-1 of
-// the upper triangle) are cut into gridDim.x contiguous ranges of equal length (+-1 tile): perfectly balanced whatever
-// the row lengths are (a round-robin deal of strips aliased with the strip-length pattern: measured 2x between the
-// busiest and the idlest SM), and a CTA walks whole rows, so the A tile of a row block is fetched once.  A "strip" is a
-// maximal run of tiles of one row block inside a range.  The producer lane and the epilogue warps iterate the same
-// sequence.
+// tile schedule: a work item is a strip = (problem b, row block I of 128, S consecutive 64-column blocks J of the
+// upper triangle, J >= 2I).  CTA c walks items c, c + gridDim.x, ...; the producer lane and the epilogue warps iterate
+// the same sequence.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline int tc_tiles_per_problem(int n) {
-  const int nt = (n + kTile - 1) / kTile;
-  return nt * tc_nt64(n) - nt * (nt - 1);
-}
-
 struct TileIter {
-  int remaining, nt, nt64;
-  int b, I, J;
-  bool first, started;
-  __device__ __forceinline__ void init(int cta, int ctas, long long total_tiles, int n) {
+  int item, step, total, spp, S, nt, nt64;
+  int b, I, J, J1;
+  bool first;
+  __device__ __forceinline__ void init(int start, int step_, int total_, int spp_, int S_, int n) {
+    item = start - step_;
+    step = step_;
+    total = total_;
+    spp = spp_;
+    S = S_;
     nt = (n + kTile - 1) / kTile;
     nt64 = tc_nt64(n);
-    const long long t0 = total_tiles * cta / ctas, t1 = total_tiles * (cta + 1) / ctas;
-    remaining = (int)(t1 - t0);
-    const int tpp = tc_tiles_per_problem(n);
-    b = (int)(t0 / tpp);
-    int r = (int)(t0 - (long long)b * tpp);
-    I = 0;
-    while (r >= nt64 - 2 * I) {
-      r -= nt64 - 2 * I;
-      ++I;
-    }
-    J = 2 * I + r;
+    b = I = 0;
+    J = J1 = 0;
     first = false;
-    started = false;
   }
   __device__ __forceinline__ bool next() {
-    if (remaining == 0) return false;
-    --remaining;
-    if (!started) {
-      started = true;
-      first = true;
+    if (J + 1 < J1) {
+      ++J;
+      first = false;
       return true;
     }
-    first = false;
-    if (++J == nt64) {
-      if (++I == nt) {
-        I = 0;
-        ++b;
-      }
-      J = 2 * I;
-      first = true;
+    item += step;
+    if (item >= total) return false;
+    b = item / spp;
+    int p = item - b * spp;
+    I = 0;
+    while (true) {
+      const int ng = (nt64 - 2 * I + S - 1) / S;
+      if (p < ng) break;
+      p -= ng;
+      ++I;
     }
+    J = 2 * I + p * S;
+    J1 = min(nt64, J + S);
+    first = true;
     return true;
   }
-  __device__ __forceinline__ bool last_of_strip() const { return J + 1 == nt64 || remaining == 0; }
+  __device__ __forceinline__ bool last_of_strip() const { return J + 1 == J1; }
 };
+
+__host__ __device__ inline int tc_strips_per_problem(int n, int S) {
+  const int nt = (n + kTile - 1) / kTile, nt64 = tc_nt64(n);
+  int total = 0;
+  for (int I = 0; I < nt; ++I) total += (nt64 - 2 * I + S - 1) / S;
+  return total;
+}
 
 // packed FP32x2 (two pairs per instruction; FADD2 / FMUL2 / FFMA2)
 typedef unsigned long long f32x2;
@@ -220,14 +212,14 @@ struct TcConsts {
   f32x2 nc2, b4, kap, c0;  // -2 beta^2, beta^4, band slope, band offset (prep_kernel)
 };
 
-// 8 pairs (columns c0 .. c0+7 of the warp's 32; call with the highest group first).  Per pair, packed two at a time:
+// 16 pairs (columns c0 .. c0+15 of the warp's 32; call with the upper half first).  Per pair, packed two at a time:
 //   t = a - b, s = a + b, P = t^2 + beta^4, d = P - 2 beta^2 s  [= (g^2 - beta^2)(w - beta^2)],  band = kap P + c0,
 //   d_hi = d + band  (sign bit 1: surely an edge),   d_lo = d - band  (sign bit 0: surely not an edge)
 // = 7 FP32 lane operations, no MUFU, no compare; the two sign bits are funnel-shifted into the words.
-__device__ __forceinline__ void tc_sweep8(const uint32_t (&ra)[8], const uint32_t (&rb)[8], const TcConsts& k,
-                                          uint32_t& whi, uint32_t& wlo) {
+__device__ __forceinline__ void tc_sweep16(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const TcConsts& k,
+                                           uint32_t& whi, uint32_t& wlo) {
 #pragma unroll
-  for (int g = 3; g >= 0; --g) {
+  for (int g = 7; g >= 0; --g) {
     const f32x2 A = pk2(ra[2 * g], ra[2 * g + 1]), B = pk2(rb[2 * g], rb[2 * g + 1]);
     const f32x2 t = sub2(A, B), s = add2(A, B);
     const f32x2 P = fma2(t, t, k.b4);
@@ -266,13 +258,13 @@ enum {
   kBarAEmpty = 2,                         // [2]  MMA commit -> TMA: the strip's A tile has been read for the last time
   kBarBFull = 4,                          // [kTcBStages]  TMA -> MMA
   kBarBEmpty = kBarBFull + kTcBStages,    // [kTcBStages]  MMA commit -> TMA: stage may be overwritten
-  kBarTFull = kBarBEmpty + kTcBStages,    // [kTcTStages]  MMA commit -> epilogue: accumulator stage ready
-  kBarTEmpty = kBarTFull + kTcTStages,    // [kTcTStages]  epilogue (8 arrivals) -> MMA: the stage's values are in registers
-  kNumBars = kBarTEmpty + kTcTStages
+  kBarTFull = kBarBEmpty + kTcBStages,    // [2]  MMA commit -> epilogue: accumulator stage ready
+  kBarTEmpty = kBarTFull + 2,             // [2]  epilogue (8 arrivals) -> MMA: accumulator stage drained
+  kNumBars = kBarTEmpty + 2
 };
 
 template <bool kVerify>
-__global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batch bt, long long total_tiles) {
+__global__ void __launch_bounds__(kTcThreads, 2) graph_tc_kernel(Batch bt, int S, int spp, int total_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcTileA + kTcBStages * kTcTileB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
@@ -286,37 +278,30 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
     for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), i >= kBarTEmpty ? kTcEpiWarps : 1);
     mbar_fence_init();
   }
-  if (warp == kTcEpiWarps) tmem_alloc<kTcTmemCols>(smem_u32(tmem_slot));
+  if (warp == kTcEpiWarps) tmem_alloc<256>(smem_u32(tmem_slot));
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;  // accumulator stage s: a at columns 128 s .. +63, b at 128 s + 64 .. +63
 
   if (warp == kTcEpiWarps) {
-    // ================= producer: TMA loads (up to kTcBStages tiles ahead), MMA issue =================
-    // One warp does both (a tenth warp would cost the 72-register budget of 3 CTAs per SM: measured, the spills of the
-    // 64-register build sat on the epilogue's critical path), so a load may only wait for commits of MMAs that have
-    // ALREADY been issued (B stage of tile n_loaded - kTcBStages, A buffer of the strip before the previous one): the
-    // loads run at most kTcBStages tiles and one strip ahead of the MMAs.
-    // All 32 lanes walk the schedule (warp-uniform values live in uniform registers: no per-MMA broadcast loops), lane 0
-    // alone issues the copies, the MMAs and the commits.
-    {
-      const bool issuer = lane == 0;
+    // ================= producer: TMA loads (kTcBStages - 1 tiles ahead), MMA issue =================
+    if (lane == 0) {
       const uint8_t* opnd = reinterpret_cast<const uint8_t*>(bt.opnd);
       const size_t per_problem = tc_a_bytes(n) + tc_b_bytes(n), a_bytes = tc_a_bytes(n);
       TileIter ld, mm;
-      ld.init(blockIdx.x, gridDim.x, total_tiles, n);
-      mm.init(blockIdx.x, gridDim.x, total_tiles, n);
+      ld.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
+      mm.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
       uint32_t n_loaded = 0, n_strips_loaded = 0, n_mma = 0, n_strips = 0, ap = 0;
-      int ld_b = -1, mm_b = -1;
-      bool ld_ok = false, mm_ok = false;
-      auto next_tc = [&](TileIter& t, int& cur_b, bool& ok) {  // next tile of a problem that takes the tensor-core path
+      int tc_b = -1;
+      bool tc_ok = false;
+      auto next_tc = [&](TileIter& t) {  // next tile of a problem that takes the tensor-core path
         while (t.next()) {
-          if (t.b != cur_b) {
-            cur_b = t.b;
-            ok = bt.gc[t.b].use_tc != 0;
+          if (t.b != tc_b) {
+            tc_b = t.b;
+            tc_ok = bt.gc[t.b].use_tc != 0;
           }
-          if (ok) return true;
+          if (tc_ok) return true;
         }
         return false;
       };
@@ -328,63 +313,54 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
           // A buffer (strip index & 1): wait until the strip that used it two strips ago has been read completely
           const uint32_t a = n_strips_loaded & 1u;
           if (n_strips_loaded >= 2) mbar_wait(bar(kBarAEmpty + a), ((n_strips_loaded >> 1) - 1) & 1u);
-          if (issuer) {
-            mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
-            bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
-          }
+          mbar_arrive_expect_tx(bar(kBarAFull + a), kTcTileA);
+          bulk_g2s(sA0 + a * kTcTileA, pb + (size_t)t.I * kTcTileA, kTcTileA, bar(kBarAFull + a));
           ++n_strips_loaded;
         }
-        if (issuer) {
-          mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
-          bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
-        }
+        mbar_arrive_expect_tx(bar(kBarBFull + st), kTcTileB);
+        bulk_g2s(sB0 + st * kTcTileB, pb + a_bytes + (size_t)t.J * kTcTileB, kTcTileB, bar(kBarBFull + st));
         ++n_loaded;
       };
       const uint32_t idesc = make_idesc_tf32(128, kTcN);
-      // K-major, no swizzle: leading byte offset = distance of the two 16-byte K-chunks (planes), stride byte offset
-      // = distance of consecutive 8-row groups (128 B).  The start address sits in the low 14 bits (>> 4): the
-      // descriptors of the other buffers / clouds / K-steps are this one plus a constant.
-      const uint64_t descA = make_smem_desc(sA0, kTcPlaneA, 128), descB = make_smem_desc(sB0, kTcPlaneB, 128);
-      bool pend = next_tc(ld, ld_b, ld_ok);
-      // tile n_loaded goes to the stage tile n_loaded - kTcBStages was read from: its MMAs must have been issued (the wait
-      // inside issue_load then only lasts until they complete); a new strip's A tile needs the strip before the previous
-      // one to have been issued completely, i.e. the previous one to have started
+      // The loads run ahead of the MMAs by at most kTcBStages - 1 tiles and at most one strip: this thread issues both,
+      // so a load may only wait for commits of MMAs that have ALREADY been issued (B stage of tile n_loaded - kTcBStages,
+      // A buffer of the strip before the previous one) — otherwise it would wait for itself.
+      bool pend = next_tc(ld);
       auto can_load = [&]() {
-        return pend && (n_loaded - n_mma) < (uint32_t)kTcBStages && (!ld.first || n_strips >= n_strips_loaded);
+        return pend && (n_loaded - n_mma) < (uint32_t)(kTcBStages - 1) && (!ld.first || n_strips >= n_strips_loaded);
       };
       while (can_load()) {
         issue_load(ld);
-        pend = next_tc(ld, ld_b, ld_ok);
+        pend = next_tc(ld);
       }
-      while (next_tc(mm, mm_b, mm_ok)) {
+      while (next_tc(mm)) {
         const uint32_t st = n_mma % kTcBStages, use = n_mma / kTcBStages;
+        const uint32_t ts = n_mma & 1u, tuse = n_mma >> 1;
         if (mm.first) {
           ap = n_strips & 1u;
           mbar_wait(bar(kBarAFull + ap), (n_strips >> 1) & 1u);
           ++n_strips;
         }
         mbar_wait(bar(kBarBFull + st), use & 1u);
-        // Everything the MMAs need is formed BEFORE the wait for the accumulators: this thread shares its scheduler with six
-        // busy epilogue warps (one instruction every ~10-15 clk), and whatever sits between that wait and the last commit is
-        // serial time in which all eight epilogue warps of the CTA wait for the next tile (measured: 134 instructions there
-        // cost 35 % of the kernel).
-        const uint64_t da0 = descA + (uint64_t)((ap * kTcTileA) >> 4), db0 = descB + (uint64_t)((st * kTcTileB) >> 4);
-        const uint32_t ts = n_mma % kTcTStages, tuse = n_mma / kTcTStages;
-        if (tuse > 0) mbar_wait(bar(kBarTEmpty + ts), (tuse - 1) & 1u);  // the epilogue has this stage's previous tile in registers
+        if (tuse > 0) mbar_wait(bar(kBarTEmpty + ts), (tuse - 1) & 1u);  // the epilogue has drained this accumulator stage
         fence_after_sync();
-        if (issuer) {
+        // K-major, no swizzle: leading byte offset = distance of the two 16-byte K-chunks (planes), stride byte offset
+        // = distance of consecutive 8-row groups (128 B)
 #pragma unroll
-          for (int c = 0; c < 6; ++c)
-            mma_tf32(tbase + 128u * ts + (uint32_t)kTcN * (c / 3), da0 + (uint64_t)(((c / 3) * kTcCloudA + (c % 3) * 2 * kTcPlaneA) >> 4),
-                     db0 + (uint64_t)(((c / 3) * kTcCloudB + (c % 3) * 2 * kTcPlaneB) >> 4), idesc, (c % 3) > 0);
-          mma_commit(bar(kBarBEmpty + st));
-          if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
-          mma_commit(bar(kBarTFull + ts));
-        }
+        for (int cloud = 0; cloud < 2; ++cloud)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint64_t da = make_smem_desc(sA0 + ap * kTcTileA + cloud * kTcCloudA + s * 2 * kTcPlaneA, kTcPlaneA, 128);
+            const uint64_t db = make_smem_desc(sB0 + st * kTcTileB + cloud * kTcCloudB + s * 2 * kTcPlaneB, kTcPlaneB, 128);
+            mma_tf32(tbase + 128u * ts + (uint32_t)kTcN * cloud, da, db, idesc, s > 0);
+          }
+        mma_commit(bar(kBarBEmpty + st));
+        if (mm.last_of_strip()) mma_commit(bar(kBarAEmpty + ap));  // the strip's A tile has been read for the last time
+        mma_commit(bar(kBarTFull + ts));
         ++n_mma;
         while (can_load()) {
           issue_load(ld);
-          pend = next_tc(ld, ld_b, ld_ok);
+          pend = next_tc(ld);
         }
       }
     }
@@ -394,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     TileIter ti;
-    ti.init(blockIdx.x, gridDim.x, total_tiles, n);
+    ti.init(blockIdx.x, gridDim.x, total_items, spp, S, n);
     uint32_t n_t = 0;
     int rdeg = 0;
     const int P32 = pitch32(n);
@@ -402,6 +378,9 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
     kc.nc2 = kc.b4 = kc.kap = kc.c0 = pk2f(0.f, 0.f);
     const GraphConsts* gcp = bt.gc;
     bool use_tc = false;
+    uint32_t* adj32 = nullptr;  // bitset of the strip's problem
+    uint32_t* rowp = nullptr;   // row i of it
+    int* degp = nullptr;
     int i = 0;
     bool row_ok = false, row_edge = false;
     while (ti.next()) {
@@ -417,12 +396,15 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
         kc.kap = pk2f(gcp->tc_kap, gcp->tc_kap);
         kc.c0 = pk2f(gcp->tc_c0, gcp->tc_c0);
         i = I * kTile + 32 * q + lane;
+        adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)ti.b * n * P32;
+        rowp = adj32 + (size_t)i * P32;
+        degp = bt.deg + (size_t)ti.b * n;
         row_ok = i < n;
         row_edge = I * kTile + kTile > n;  // some rows of the block lie past n
       }
       const int j0 = J * kTcN + 32 * h;
-      const uint32_t ts = n_t % kTcTStages;
-      mbar_wait(bar(kBarTFull + ts), (n_t / kTcTStages) & 1u);
+      const uint32_t ts = n_t & 1u;
+      mbar_wait(bar(kBarTFull + ts), (n_t >> 1) & 1u);
       fence_after_sync();
       const uint32_t ta = tbase + lane_base + 128u * ts + 32u * (uint32_t)h, tb = ta + (uint32_t)kTcN;
       // ---- sweep: whi bit k = pair (i, j0+k) surely an edge, wlo bit k = not surely a non-edge.  The second half of the
@@ -436,14 +418,12 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
         tmem_wait_ld();
         tmem_ld16(ta, a0);
         tmem_ld16(tb, b0);
-        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a1[8]), reinterpret_cast<const uint32_t(&)[8]>(b1[8]), kc, whi, wlo);
-        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a1[0]), reinterpret_cast<const uint32_t(&)[8]>(b1[0]), kc, whi, wlo);
+        tc_sweep16(a1, b1, kc, whi, wlo);
         tmem_wait_ld();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kBarTEmpty + ts));
-        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a0[8]), reinterpret_cast<const uint32_t(&)[8]>(b0[8]), kc, whi, wlo);
-        tc_sweep8(reinterpret_cast<const uint32_t(&)[8]>(a0[0]), reinterpret_cast<const uint32_t(&)[8]>(b0[0]), kc, whi, wlo);
+        tc_sweep16(a0, b0, kc, whi, wlo);
       }
       // validity of the pairs of this thread: columns < n, row < n, i != j (interior tiles: everything valid)
       uint32_t vmask = 0xffffffffu;
@@ -513,10 +493,8 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
           }
         }
       }
-      uint32_t* adj32 = reinterpret_cast<uint32_t*>(bt.adj) + (size_t)ti.b * ((size_t)n * P32);  // bitset of the problem
-      int* degp = bt.deg + (size_t)ti.b * n;
       rdeg += __popc(word);
-      if (row_ok) adj32[(size_t)i * P32 + 2 * J + h] = word;
+      if (row_ok) rowp[2 * J + h] = word;
       if (!diag) {  // transposed half: lane l holds column j0+l over rows I*128 + 32q .. +31
         const uint32_t colw = tc_transpose32(word, lane);
         const int jc = j0 + lane;
@@ -534,7 +512,7 @@ __global__ void __launch_bounds__(kTcThreads, kTcCtasPerSm) graph_tc_kernel(Batc
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == kTcEpiWarps) tmem_dealloc<kTcTmemCols>(tbase);
+  if (warp == kTcEpiWarps) tmem_dealloc<256>(tbase);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -577,22 +555,23 @@ int launch_graph_tc(const Batch& bt, cudaStream_t st, int num_sms) {
   if (!attr_done_dev[dev & 63]) {
     cudaFuncSetAttribute(graph_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     cudaFuncSetAttribute(graph_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    // two CTAs of 96 KB per SM
-    cudaFuncSetAttribute(graph_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(graph_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done_dev[dev & 63] = true;
   }
   const int nt = (bt.n + kTile - 1) / kTile;
   dim3 pg((unsigned)nt, (unsigned)bt.B);
   cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);
   tc_prep_kernel<<<pg, 128, 0, st>>>(bt);
-  const int ctas = kTcCtasPerSm * num_sms;
-  const long long total = (long long)bt.B * tc_tiles_per_problem(bt.n);
+  // strip length (in 64-column tiles): long strips amortise the A tile, short ones balance small batches
+  const int ctas = 2 * num_sms;
+  int S = 16;
+  while (S > 1 && (long long)bt.B * tc_strips_per_problem(bt.n, S) < 4LL * ctas) S >>= 1;
+  const int spp = tc_strips_per_problem(bt.n, S);
+  const long long total = (long long)bt.B * spp;
   const int grid = (int)(total < ctas ? total : ctas);
   if (bt.flags_dbg & 2u)
-    graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, total);
+    graph_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
   else
-    graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, total);
+    graph_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(bt, S, spp, (int)total);
   tc_patch_kernel<<<4 * num_sms, 256, 0, st>>>(bt);
   cudaMemsetAsync(bt.tc_list_count, 0, sizeof(unsigned int), st);  // the strip kernel (other problems) queues next
   return 3;

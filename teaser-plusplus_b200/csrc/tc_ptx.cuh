@@ -93,16 +93,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-// 32 lanes x 8 columns
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-      : "r"(taddr)
-      : "memory");
-}
-
 // ---- descriptors -----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major operand, no swizzle ("interleave"): the operand is a grid of 8-row x
 // 16-byte core matrices (rows 16 B apart inside a core matrix);
