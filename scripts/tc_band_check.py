@@ -7,7 +7,7 @@ sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(_
 synth=importlib.import_module("teaser-plusplus_b200.synth")
 u=2.0**-24
 def f32(x): return np.asarray(x,dtype=np.float64).astype(np.float32).astype(np.float64)
-def check(src,dst,nb,mode,label):
+def check(src,dst,nb,mode,label,verbose=True):
     n=len(src); beta=2*nb
     mn=src.min(0);mx=src.max(0);Ds2=((mx-mn)**2).sum()
     mn=dst.min(0);mx=dst.max(0);Dd2=((mx-mn)**2).sum()
@@ -36,20 +36,27 @@ def check(src,dst,nb,mode,label):
     sure_non=~maybe
     bad1=(sure_edge&~exact).sum(); bad2=(sure_non&exact).sum()
     und=(maybe&~sure_edge).sum()
-    print(f"{label:10s} {mode:4s} use_tc={ok} pairs={len(a)} edges={exact.sum()} undecided={und} ({und/len(a):.2e}) wrong_edge={bad1} wrong_non={bad2}")
-    return bad1+bad2
-tot=0
-for cfg,n in [("C2",1500),("C2cube",1100),("C3",2000),("C4",640),("C5",1700)]:
-    pr=synth.config_problem(cfg,21,n=n)
-    for mode in ['rand','pp','pm','mm','x']:
-        tot+=check(pr['src'],pr['dst'],pr['noise_bound'],mode,cfg)
-# duplicates / short TIMs
-pr=synth.config_problem("C2cube",8,n=700); src,dst=pr['src'].copy(),pr['dst'].copy()
-for k in range(0,60,3): src[k+1]=src[k]
-for k in range(100,160,3): dst[k+1]=dst[k]; src[k+1]=src[k]+1e-9
-for mode in ['rand','pp','pm']: tot+=check(src,dst,pr['noise_bound'],mode,'dups')
-# big beta (beyond guard) to exercise s<=beta^2 clause
-pr=synth.config_problem("C2",3,n=600)
-for nb in [0.05,0.2,0.5]:
-    for mode in ['rand','pm','pp']: tot+=check(pr['src'],pr['dst'],nb,mode,f'nb{nb}')
-print('TOTAL WRONG',tot)
+    if verbose: print(f"{label:10s} {mode:4s} use_tc={ok} pairs={len(a)} edges={exact.sum()} undecided={und} ({und/len(a):.2e}) wrong_edge={bad1} wrong_non={bad2}")
+    return int(bad1+bad2), float(und/len(a)), bool(ok)
+def check_(*a):
+    return check(*a)[0]
+
+def main():
+    tot=0
+    for cfg,n in [("C2",1500),("C2cube",1100),("C3",2000),("C4",640),("C5",1700)]:
+        pr=synth.config_problem(cfg,21,n=n)
+        for mode in ['rand','pp','pm','mm','x']:
+            tot+=check_(pr['src'],pr['dst'],pr['noise_bound'],mode,cfg)
+    # duplicates / short TIMs
+    pr=synth.config_problem("C2cube",8,n=700); src,dst=pr['src'].copy(),pr['dst'].copy()
+    for k in range(0,60,3): src[k+1]=src[k]
+    for k in range(100,160,3): dst[k+1]=dst[k]; src[k+1]=src[k]+1e-9
+    for mode in ['rand','pp','pm']: tot+=check_(src,dst,pr['noise_bound'],mode,'dups')
+    # big beta (beyond guard) to exercise s<=beta^2 clause
+    pr=synth.config_problem("C2",3,n=600)
+    for nb in [0.05,0.2,0.5]:
+        for mode in ['rand','pm','pp']: tot+=check_(pr['src'],pr['dst'],nb,mode,f'nb{nb}')
+    print('TOTAL WRONG',tot)
+
+if __name__ == "__main__":
+    main()

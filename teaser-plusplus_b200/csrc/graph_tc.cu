@@ -17,15 +17,16 @@
 // completion on mbarriers; the accumulators are double-buffered in TMEM so the MMAs of tile t+1 run under the
 // epilogue of tile t.
 //
-// Epilogue (8 warps, tcgen05.ld 32 lanes x 16 columns): with t = a-b, s = a+b, q = sqrt(ab) (one MUFU per pair)
-//     d = t^2 - beta^2 (s + 2q) = (sqrt a + sqrt b)^2 (g^2 - beta^2),      g = |sqrt a - sqrt b|
-// so the pair is an edge iff d <= 0.  This form is well conditioned (both sides are equal at the threshold, so the
-// FP32 evaluation error is a few ulp of beta^2 (sqrt a + sqrt b)^2, no cancellation of D^2-sized terms against
-// beta^2).  The sign bit of d is shifted straight into the row word (no compare, no ballot); whether any of the
-// thread's 32 pairs falls into the error band of the tensor-core norms (d^2 <= t^2 (k1 + k2 t^2), or a tiny a / b;
-// prep_kernel) is tracked with three 3-input FMNMX, and only then the warp revisits its chunk (re-read
-// from TMEM) and queues the flagged pairs; tc_patch_kernel re-evaluates them with the reference's exact FP64 sequence.  7 issue slots + 1 MUFU per
-// pair instead of ~20 + 2.
+// Epilogue (8 warps, tcgen05.ld 32 lanes x 16 columns): with t = a-b, s = a+b, g = |sqrt a - sqrt b|, w = (sqrt a + sqrt b)^2
+//     f = t^2 - 2 beta^2 s + beta^4 = (g^2 - beta^2)(w - beta^2)          edge  <=>  s <= beta^2  or  f <= 0
+// a polynomial in the tensor-core values: no square root, no division, and its error is a Lipschitz bound
+// (|f' - f| <= 2 E |t'| + E^2 + 2 beta^2 E for |a' - a| + |b' - b| <= E), so there are no guards for tiny norms.  Per pair,
+// packed two at a time: t, s, P = t^2 + beta^4, d = P - 2 beta^2 s, band = kap P + c0, d + band, d - band = 7 FP32
+// lane operations; the two sign bits are funnel-shifted into the words whi (surely an edge) and wlo (not surely a
+// non-edge) — no compare, no ballot, no MUFU.  whi is the tentative row word; wlo & ~whi are the pairs inside the error
+// band (prep_kernel, DESIGN.md §3.1: 3.5e-5 of the pairs on C2): they are queued and tc_patch_kernel re-evaluates them
+// with the reference's exact FP64 sequence.  The accumulator stage goes back to the MMA issuer as soon as the warp's
+// values sit in registers.
 // Output (packed symmetric bitset, fused degrees) is bit-identical to graph_build.cu's and to the oracle's.
 #include "tc_ptx.cuh"
 #include "tzr_internal.cuh"

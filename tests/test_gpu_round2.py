@@ -77,7 +77,8 @@ def test_v7_strip_kernel_bit_exact(ctx, cfg, n):
 
 def test_tc_kernel_falls_back_when_ill_conditioned(ctx):
     """A noise bound that is tiny against the extent of the clouds (C1-like: beta/D ~ 1e-4) makes the tensor-core
-    filter's undecided band wider than beta/4: prep_kernel routes the problem to the CUDA-core kernel; bits stay exact."""
+    filter's undecided band (E / (0.75 D) in |sqrt a - sqrt b|) wider than beta/64: prep_kernel routes the problem to the
+    CUDA-core kernel; bits stay exact."""
     pr = synth.config_problem("C2", 4, n=400)
     src, dst = pr["src"].copy(), pr["dst"].copy()
     dst[::7] += 300.0
@@ -92,8 +93,9 @@ def test_tc_kernel_falls_back_when_ill_conditioned(ctx):
 
 
 def test_tc_kernel_duplicates_coincident_points(ctx):
-    """Zero-length TIMs (duplicate correspondences): a' = 0 +- error can come out negative (sqrt of a negative
-    product) — those pairs must land in the exact path, not in a wrong bit."""
+    """Zero-length TIMs (duplicate correspondences): a' = 0 +- error can come out negative, and with s = a + b <= beta^2
+    the sign of the polynomial says nothing — those pairs must land in the exact path (the beta^4 floor of the band), not in
+    a wrong bit."""
     pr = synth.config_problem("C2cube", 8, n=700)
     src, dst = pr["src"].copy(), pr["dst"].copy()
     for k in range(0, 60, 3):
