@@ -267,14 +267,18 @@ int tzr_solve_batch_multi(const int32_t* devices, int n_devices, const tzr_param
  * bit 2 (4) = count exact re-checks and clique search nodes, bit 8 (256) = degrees by a separate pass,
  * bit 10 (1024) = build the graph with the tensor-core kernel (tcgen05 Gram norms; bit-identical, measured slower than
  * the default CUDA-core kernel on B200: DESIGN.md 3.1), bit 9 (512) overrides it, bit 11 (2048) = the one-MUFU
- * CUDA-core variant (graph_strip3_kernel; bit-identical, FMA-pipe bound, 8 % slower). */
+ * CUDA-core variant (graph_strip3_kernel; bit-identical, FMA-pipe bound, 8 % slower), bit 13 (8192) = exact clique
+ * search without the singleton-class path of the colouring (A/B), bit 12 (4096) = without the block colour bound (only
+ * present in builds with -DTZR_BLOCK_BOUND). */
 int tzr_ctx_set_flags(tzr_ctx* ctx, uint32_t flags);
 int64_t tzr_ctx_filter_mismatches(tzr_ctx* ctx);
 /* Number of pairs of the most recent graph build that needed the exact FP64 re-check. */
 int64_t tzr_ctx_filter_rechecks(tzr_ctx* ctx);
 /* Debug counters of the most recent call (flag bit 2 set): [0] filter mismatches, [1] filter re-checks, [2] clique
  * search nodes, [3] reduce rounds, [4] vertices scanned by reduce rounds, [5] colourings, [6] vertices coloured,
- * [7] problems whose graph was built by the tensor-core kernel. */
+ * [7] problems whose graph was built by the tensor-core kernel, [8]-[10] clock cycles of the exact search in the root
+ * colour bound / degree rules / colourings, [11] slowest root (ns << 16 | vertex), [12] summed root time (ns),
+ * [13] roots above 1 ms, [14] roots closed by the block colour bound. */
 int tzr_ctx_debug_counters(tzr_ctx* ctx, int64_t* out16);
 
 #ifdef __cplusplus
